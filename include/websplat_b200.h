@@ -1,0 +1,237 @@
+/*
+ * websplat_b200.h -- C ABI of the B200-native splat render path.
+ *
+ * This is the drop-in boundary for the ONE hot path of KeKsBoTer/web-splat:
+ * GaussianRenderer::prepare + GaussianRenderer::render and the PointCloud GPU
+ * layout they consume.  The reference exposes that path as a Rust struct API
+ * (no FFI exists upstream); each entry point below names the reference item it
+ * replaces (paths relative to the reference repo root).  INTEGRATION.md shows
+ * the Rust `extern "C"` binding + safe wrapper that keeps the reference's names.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; opaque handles; no C++/torch/CUDA types.
+ *    `cuda_stream` parameters are a `cudaStream_t` passed as `void*` (NULL =
+ *    the legacy default stream).  This is the analogue of "records into the
+ *    caller's CommandEncoder": all device work is enqueued on that stream and
+ *    nothing blocks unless the call is documented as synchronising.
+ *  - every function returns ws_status (0 = OK, negative = error); no exceptions
+ *    or aborts cross the boundary (the reference unwrap()s / panics instead).
+ *  - a ws_renderer is not re-entrant (same as `&mut self` in renderer.rs:191):
+ *    one host thread per renderer handle, frames serialised by the caller.
+ *  - there is no CPU fallback: every entry point that does work needs a CUDA
+ *    device of compute capability 10.x and fails with WS_ERR_CUDA otherwise.
+ */
+#ifndef WEBSPLAT_B200_H
+#define WEBSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define WS_API
+#else
+#define WS_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t ws_status;
+enum {
+    WS_OK = 0,
+    WS_ERR_INVALID_ARGUMENT = -1,
+    WS_ERR_CUDA = -2,            /* a CUDA runtime call failed / no usable device */
+    WS_ERR_OUT_OF_MEMORY = -3,
+    WS_ERR_PAIR_OVERFLOW = -4,   /* (tile, splat) pairs exceeded the pair capacity; frame incomplete */
+    WS_ERR_NOT_PREPARED = -5,    /* render() without a preceding prepare() */
+    WS_ERR_UNSUPPORTED = -6,
+    WS_ERR_MISMATCH = -7         /* point cloud does not match the renderer's (sh_deg, compressed) */
+};
+WS_API const char *ws_status_string(ws_status s);
+/* text of the last CUDA error seen by this thread's most recent failing call ("" if none) */
+WS_API const char *ws_last_error(void);
+
+typedef struct ws_context ws_context;       /* ~ WGPUContext (src/lib.rs:68-126): device + queue */
+typedef struct ws_pointcloud ws_pointcloud; /* ~ PointCloud (src/pointcloud.rs:72-88) */
+typedef struct ws_renderer ws_renderer;     /* ~ GaussianRenderer (src/renderer.rs:17-31) */
+
+/* ---- context ---------------------------------------------------------------
+ * replaces WGPUContext::new_instance (src/lib.rs:69-76): picks the device. */
+WS_API ws_status ws_context_create(int cuda_device, ws_context **out);
+WS_API void ws_context_destroy(ws_context *ctx);
+WS_API int ws_context_device(const ws_context *ctx);
+WS_API int ws_context_sm_count(const ws_context *ctx);
+
+/* ---- value types -------------------------------------------------------- */
+typedef struct { float min[3]; float max[3]; } ws_aabb;              /* Aabb<f32>, src/pointcloud.rs:398-403 */
+typedef struct { int32_t zero_point; float scale; uint32_t _pad[2]; } ws_quantization;   /* src/pointcloud.rs:360-366 */
+typedef struct { ws_quantization color_dc, color_rest, opacity, scaling_factor; } ws_quantization4; /* :389-396 */
+
+/* GenericGaussianPointCloud (src/io/mod.rs:27-42): the CPU byte buffers in the
+ * exact GPU layouts the reference uploads, plus metadata. */
+typedef struct {
+    const void *gaussians;      /* num_points x 28 B `Gaussian` (src/pointcloud.rs:38-45) or, compressed,
+                                   num_points x 24 B `GaussianCompressed` (src/pointcloud.rs:14-24) */
+    uint64_t num_points;
+    const void *sh_coefs;       /* raw: num_points x 96 B [[f16;3];16] (src/io/mod.rs:65);
+                                   compressed: i8, (sh_deg+1)^2*3 B per entry (src/io/npz.rs:183-196) */
+    uint64_t sh_bytes;
+    const void *covars;         /* compressed only: num_covars x 12 B `Covariance3D` (src/pointcloud.rs:63) */
+    uint64_t num_covars;
+    const ws_quantization4 *quantization;   /* compressed only */
+    uint32_t sh_deg;
+    uint32_t compressed;
+    ws_aabb aabb;
+    float center[3];
+    int32_t has_up;  float up[3];
+    int32_t has_mip_splatting; int32_t mip_splatting;
+    int32_t has_kernel_size;   float kernel_size;
+    int32_t has_background;    float background_color[3];
+} ws_pointcloud_desc;
+
+/* ---- PointCloud ------------------------------------------------------------
+ * replaces PointCloud::new (src/pointcloud.rs:99-199).  Copies the host buffers to
+ * HBM (synchronous); the caller keeps ownership of its memory. */
+WS_API ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_desc *desc, ws_pointcloud **out);
+WS_API void ws_pointcloud_destroy(ws_pointcloud *pc);
+/* getters, src/pointcloud.rs:201-349 */
+WS_API uint32_t ws_pointcloud_num_points(const ws_pointcloud *pc);
+WS_API uint32_t ws_pointcloud_sh_deg(const ws_pointcloud *pc);
+WS_API int32_t ws_pointcloud_compressed(const ws_pointcloud *pc);
+WS_API ws_status ws_pointcloud_bbox(const ws_pointcloud *pc, ws_aabb *out);
+WS_API ws_status ws_pointcloud_center(const ws_pointcloud *pc, float out[3]);
+WS_API int32_t ws_pointcloud_up(const ws_pointcloud *pc, float out[3]);                 /* returns has_up */
+WS_API int32_t ws_pointcloud_mip_splatting(const ws_pointcloud *pc, int32_t *out);      /* returns has_value */
+WS_API int32_t ws_pointcloud_dilation_kernel_size(const ws_pointcloud *pc, float *out); /* returns has_value */
+
+/* ---- camera helpers (host only, no device work) ----------------------------
+ * Aabb::center / Aabb::radius (src/pointcloud.rs:441-448) and
+ * PerspectiveCamera::fit_near_far (src/camera.rs:26-35). */
+WS_API void ws_aabb_center(const ws_aabb *b, float out[3]);
+WS_API float ws_aabb_radius(const ws_aabb *b);
+WS_API void ws_camera_fit_near_far(const float position[3], const ws_aabb *aabb, float *znear, float *zfar);
+
+/* ---- GaussianRenderer ---------------------------------------------------- */
+typedef enum {            /* the three wgpu::TextureFormat values the reference's callers use */
+    WS_FORMAT_RGBA8_UNORM = 0,   /* viewer default src/lib.rs:192-196, bin/measure.rs:184 */
+    WS_FORMAT_RGBA16_FLOAT = 1,  /* --hdr, bin/render.rs:154 */
+    WS_FORMAT_RGBA32_FLOAT = 2   /* bin/video.rs:186 */
+} ws_format;
+
+/* replaces GaussianRenderer::new (src/renderer.rs:33-123): specialised on
+ * (format, sh_deg, compressed); serves any cloud with those properties. */
+WS_API ws_status ws_renderer_create(ws_context *ctx, ws_format color_format, uint32_t sh_deg,
+                                    int32_t compressed, ws_renderer **out);
+WS_API void ws_renderer_destroy(ws_renderer *r);
+WS_API ws_format ws_renderer_color_format(const ws_renderer *r);        /* src/renderer.rs:281-283 */
+
+/* SplattingArgs (src/renderer.rs:587-599).  Option<T> fields become has_* flags. */
+typedef struct {
+    /* PerspectiveCamera (src/camera.rs:7-11) */
+    float cam_position[3];
+    float cam_rotation_wxyz[4];   /* cgmath Quaternion::new(w, xi, yj, zk); Matrix3::from(q) = world->camera */
+    /* PerspectiveProjection (src/camera.rs:86-94); fov in radians */
+    float fovx, fovy, znear, zfar, fov2view_ratio;
+    uint32_t viewport[2];
+    float gaussian_scaling;
+    uint32_t max_sh_deg;
+    int32_t has_mip_splatting; int32_t mip_splatting;
+    int32_t has_kernel_size;   float kernel_size;
+    int32_t has_clipping_box;  ws_aabb clipping_box;
+    float walltime_secs;          /* Duration::as_secs_f32 (src/renderer.rs:643) */
+    int32_t has_scene_center;  float scene_center[3];   /* ignored, as in the reference (src/renderer.rs:644) */
+    int32_t has_scene_extend;  float scene_extend;
+    double background_color[4];   /* wgpu::Color; not read by prepare (the caller clears with it) */
+} ws_splatting_args;
+
+/* replaces GaussianRenderer::prepare (src/renderer.rs:191-248): resolves the
+ * uniforms (CameraUniform src/renderer.rs:321-343, SplattingArgsUniform
+ * src/renderer.rs:620-651), (re)allocates the sort buffers when the point count
+ * changed (src/renderer.rs:200-211) and enqueues stage 1 (preprocess) + stage 2
+ * (sort; here: depth sort, tile binning, tile sort, tile ranges). Asynchronous. */
+WS_API ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
+                                     void *cuda_stream);
+
+/* replaces GaussianRenderer::render (src/renderer.rs:250-260) together with the
+ * caller's render pass (LoadOp::Clear(clear) on a target of color_format(),
+ * src/lib.rs:451-462, bin/render.rs:108-123): enqueues stage 3 and writes the
+ * finished frame to `dst_rgba` (DEVICE memory, row 0 = top row, `row_pitch_bytes`
+ * >= width * bytes-per-pixel).  Must follow prepare on the same stream. Asynchronous. */
+WS_API ws_status ws_renderer_render(ws_renderer *r, ws_pointcloud *pc, void *dst_rgba_device,
+                                    size_t row_pitch_bytes, const double clear[4], void *cuda_stream);
+
+/* render + download (bin/render.rs:187-246 download_texture): same as above into an
+ * internal device frame, then an async device->host copy into `dst_rgba_host`
+ * (pinned memory for a truly asynchronous copy).  Returns after enqueueing. */
+WS_API ws_status ws_renderer_render_to_host(ws_renderer *r, ws_pointcloud *pc, void *dst_rgba_host,
+                                            size_t row_pitch_bytes, const double clear[4], void *cuda_stream);
+
+/* replaces GaussianRenderer::num_visible_points (src/renderer.rs:170-189). Synchronises the frame. */
+WS_API ws_status ws_renderer_num_visible_points(ws_renderer *r, uint32_t *out);
+
+/* The GPUStopwatch replacement (src/utils.rs:26-134; labels "preprocess", "sorting",
+ * "rasterization": src/renderer.rs:220-239, src/lib.rs:447-467) plus counts.
+ * Synchronises the last frame.  Returns WS_ERR_PAIR_OVERFLOW (with the stats still
+ * filled in, num_pairs = pairs needed) when the frame overflowed the pair capacity. */
+typedef struct {
+    uint32_t num_points;      /* N */
+    uint32_t num_visible;     /* V */
+    uint64_t num_pairs;       /* P = sum over visible splats of 16x16 tiles touched */
+    uint64_t pair_capacity;
+    uint32_t num_tiles;       /* T */
+    uint32_t width, height;
+    float ms_preprocess;      /* stage 1 */
+    float ms_sort;            /* stage 2: depth sort + tile binning + tile sort + ranges */
+    float ms_blend;           /* stage 3 */
+    float ms_depth_sort, ms_binning, ms_tile_sort, ms_ranges;   /* breakdown of ms_sort */
+    uint64_t bytes_preprocess, bytes_sort, bytes_blend;         /* algorithmic HBM bytes */
+} ws_frame_stats;
+WS_API ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *out);
+
+/* Capacity policy for the data-dependent pair list.  0 = automatic
+ * (max(8*N, 1<<22)).  Takes effect at the next prepare(). */
+WS_API ws_status ws_renderer_set_pair_capacity(ws_renderer *r, uint64_t max_pairs);
+/* per-stage CUDA-event timing on/off (default on; costs 8 event records per frame) */
+WS_API ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled);
+
+/* ---- intermediate read-back (parity tests; synchronises) -------------------
+ * Copies an intermediate buffer of the LAST prepared frame to host memory. */
+typedef enum {
+    WS_BUF_SPLATS_2D = 0,     /* V x 20 B `Splat` (src/pointcloud.rs:352-358), slot = Gaussian-index order */
+    WS_BUF_DEPTH_KEYS = 1,    /* V x u32 sort_depths in slot order (preprocess.wgsl:273) */
+    WS_BUF_SORTED_INDICES = 2,/* V x u32 payload after the depth sort = draw order (gaussian.wgsl:37) */
+    WS_BUF_TILE_RECTS = 3,    /* V x 4 u16 {x0,y0,x1,y1} inclusive tile rect per slot (new design) */
+    WS_BUF_PAIR_TILES = 4,    /* P x u32 tile id, sorted (new design) */
+    WS_BUF_PAIR_SLOTS = 5,    /* P x u32 splat slot, sorted by (tile, depth key, slot) */
+    WS_BUF_TILE_RANGES = 6,   /* T x {u32 begin, u32 end} into the pair list */
+    WS_BUF_SORTED_KEYS = 7    /* V x u32 depth keys after the sort (ascending) */
+} ws_buffer_id;
+WS_API ws_status ws_renderer_read_buffer(ws_renderer *r, ws_buffer_id which, void *dst_host,
+                                         size_t dst_bytes, size_t *bytes_written);
+
+/* ---- the sort on its own ---------------------------------------------------
+ * replaces GPURSSorter::record_sort (src/gpu_rs.rs:865-873) as used by the
+ * reference's own self test GPURSSorter::test_sort (src/gpu_rs.rs:295-331):
+ * stable ascending sort of n (u32 key, u32 payload) pairs in DEVICE memory,
+ * in place (result lands back in keys/payload like the reference's ping-pong,
+ * radix_sort.wgsl:482-509).  `key_bits` in [1,32]: only the low key_bits are
+ * sorted (ceil(key_bits/8) onesweep passes). */
+WS_API ws_status ws_sort_pairs_u32(ws_context *ctx, uint32_t *keys_device, uint32_t *payload_device,
+                                   uint32_t n, uint32_t key_bits, void *cuda_stream);
+/* host-memory convenience wrapper (uploads, sorts, downloads; synchronous) */
+WS_API ws_status ws_sort_pairs_u32_host(ws_context *ctx, uint32_t *keys_host, uint32_t *payload_host,
+                                        uint32_t n, uint32_t key_bits);
+
+/* ---- uniforms, for inspection (renderer.rs:125, 285) ------------------------
+ * CameraUniform (272 B, src/renderer.rs:290-306) and SplattingArgsUniform
+ * (80 B, src/renderer.rs:604-619) exactly as the reference would upload them. */
+WS_API ws_status ws_renderer_camera_uniform(const ws_renderer *r, float out68[68]);
+WS_API ws_status ws_renderer_settings_uniform(const ws_renderer *r, void *out80);
+
+WS_API const char *ws_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEBSPLAT_B200_H */

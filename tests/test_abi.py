@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/websplat_b200.h declares, host-only helpers agree with the oracle, and device work fails
+LOUDLY without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "websplat_b200.h")).read()
+    return sorted(set(re.findall(r"WS_API[^;(]*?\b(ws_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(ws):
+    L = ws.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), "libwebsplat_b200.so does not export %s" % name
+    assert sorted(ws.EXPORTED_SYMBOLS) == declared
+
+
+def test_struct_layouts_match_reference_uniforms(ws):
+    # SplattingArgs mirror, stats, desc: sizes are part of the ABI
+    assert C.sizeof(ws.ws_aabb) == 24
+    assert C.sizeof(ws.ws_quantization4) == 64              # pointcloud.rs:389-396, 4 x 16 B
+    assert ws.synth.GAUSSIAN_DTYPE.itemsize == 28           # pointcloud.rs:38-45
+    assert ws.synth.GAUSSIAN_COMPRESSED_DTYPE.itemsize == 24  # pointcloud.rs:14-24
+    assert ws.synth.GAUSSIAN_DTYPE.fields["opacity"][1] == 12 and ws.synth.GAUSSIAN_DTYPE.fields["cov"][1] == 16
+    f = ws.synth.GAUSSIAN_COMPRESSED_DTYPE.fields
+    assert f["opacity"][1] == 12 and f["scale_factor"][1] == 13 and f["geometry_idx"][1] == 16 and f["sh_idx"][1] == 20
+
+
+def test_host_helpers_match_oracle(ws, orc):
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        lo = rng.uniform(-3, 0, 3).astype(np.float32); hi = rng.uniform(0, 3, 3).astype(np.float32)
+        pos = rng.uniform(-5, 5, 3).astype(np.float32)
+        box = ws.Aabb(lo, hi)
+        assert np.float32(box.radius()) == orc.aabb_radius(lo, hi)
+        cam = ws.PerspectiveCamera(pos, (1, 0, 0, 0), ws.PerspectiveProjection(1.0, 1.0, 0.1, 100.0))
+        cam.fit_near_far(box)
+        zn, zf = orc.fit_near_far(pos, lo, hi)
+        assert (np.float32(cam.projection.znear), np.float32(cam.projection.zfar)) == (np.float32(zn), np.float32(zf))
+
+
+def test_status_strings_and_version(ws):
+    L = ws.lib()
+    assert L.ws_status_string(0) == b"ok"
+    assert b"pair" in L.ws_status_string(ws.WS_ERR_PAIR_OVERFLOW)
+    assert b"sm_100a" in L.ws_version()
+
+
+def test_no_cpu_fallback_without_gpu(ws):
+    """The product must fail loudly when there is no CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ws.WsError) as e:
+        ws.Context(0)
+    assert e.value.status == ws.WS_ERR_CUDA
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "web-splat_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                for pat in (r'#\s*include\s*[<"][^>"]*oracle', r"libws_oracle", r"^\s*from\s+oracle\b", r"^\s*import\s+oracle\b", r"wso_[a-z_]+\s*\("):
+                    assert not re.search(pat, txt, re.M), (fn, pat)

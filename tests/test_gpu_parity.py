@@ -1,0 +1,233 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle.
+
+Bars (DESIGN.md "Parity"):
+  stage 1 raw layout      bit-exact (visible set, 10 halves, depth key, tile rect, V, P)
+  stage 2 sort            bit-exact (sorted keys, payload permutation, stability); reference KAT
+  binning + tile sort     bit-exact ((tile, slot) pair list, tile ranges)
+  stage 3 image           |cuda - oracle| <= 2e-3 + sens(pixel) in f32; sens = oracle's bound on
+                          contributions whose discard test a > 2*CUTOFF lies within 1e-4 of the threshold
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import image_close, make_args, make_generic, oracle_pairs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _frame(ws, ctx, cloud, pos, rot, W, H, fmt=None, clear=(0, 0, 0, 0), **kw):
+    import torch
+    fmt = ws.FORMAT_RGBA32_FLOAT if fmt is None else fmt
+    fovx, fovy = ws.synth.fov_for_viewport(W, H)
+    pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+    r = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
+    args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy, **kw)
+    r.prepare(None, pc, args)
+    dt = {0: torch.uint8, 1: torch.float16, 2: torch.float32}[fmt]
+    target = torch.empty((H, W, 4), dtype=dt, device="cuda")
+    r.render(target, pc, clear)
+    torch.cuda.synchronize()
+    return r, pc, target.cpu().numpy(), (fovx, fovy)
+
+
+def _check_all_stages(ws, orc, ctx, cloud, pos, rot, W, H, **kw):
+    r, pc, img, (fovx, fovy) = _frame(ws, ctx, cloud, pos, rot, W, H, **kw)
+    ref = orc.render_frame(cloud, pos, rot, W, H, fovx, fovy, want_sens=True, **kw)
+    st = r.stats()
+    V = len(ref["keys"])
+    # uniforms as the reference would upload them
+    assert np.array_equal(r.camera_uniform().view(np.uint32), np.frombuffer(bytes(ref["cam"]), np.uint32))
+    assert r.settings_uniform().tobytes() == bytes(ref["settings"])
+    # stage 1
+    assert st["num_visible"] == V == r.num_visible_points()
+    splats = r.read_buffer(ws.BUF_SPLATS_2D)
+    a, b = splats, ref["splats"]
+    nan_a = np.isnan(a.view(np.float16)); nan_b = np.isnan(b.view(np.float16))
+    assert np.array_equal(nan_a, nan_b)
+    assert np.array_equal(a[~nan_a], b[~nan_b]), "stage-1 halves differ from the oracle"
+    assert np.array_equal(r.read_buffer(ws.BUF_DEPTH_KEYS), ref["keys"])
+    # stage 2 (depth sort)
+    sk, order = orc.sort_pairs(ref["keys"], np.arange(V, dtype=np.uint32))
+    assert np.array_equal(r.read_buffer(ws.BUF_SORTED_KEYS), sk)
+    assert np.array_equal(r.read_buffer(ws.BUF_SORTED_INDICES), order)
+    # tile binning
+    tiles, slots, rects, P = oracle_pairs(orc, ref["splats"], order, W, H)
+    assert st["num_pairs"] == P
+    rc = r.read_buffer(ws.BUF_TILE_RECTS).astype(np.int32)
+    mine = np.stack([rc[:, 0], rc[:, 1], rc[:, 0] + rc[:, 2] - 1, rc[:, 1] + rc[:, 3] - 1], 1)
+    empty = rc[:, 2] == 0
+    assert np.array_equal(empty, rects[:, 2] < rects[:, 0])
+    assert np.array_equal(mine[~empty], rects[~empty])
+    assert np.array_equal(r.read_buffer(ws.BUF_PAIR_TILES), tiles)
+    assert np.array_equal(r.read_buffer(ws.BUF_PAIR_SLOTS), slots)
+    rng_ = r.read_buffer(ws.BUF_TILE_RANGES)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    cnt = np.bincount(tiles, minlength=T)
+    assert np.array_equal(rng_[:, 1] - rng_[:, 0], cnt)
+    # stage 3
+    d, ok = image_close(img, ref["image"], ref["sens"])
+    assert ok.all(), "image: %d px outside tolerance, max |d| %.3g" % ((~ok).sum(), d.max())
+    assert np.abs(img - ref["image"]).mean() <= 2e-5
+    return r, st, d
+
+
+def test_sort_kat_from_reference(ws, ctx):
+    """GPURSSorter::test_sort (gpu_rs.rs:295-331) through the C ABI."""
+    z = np.load(os.path.join(GOLDEN, "sort_kat.npz"))
+    keys, vals = ws.sort_pairs_host(ctx, z["keys_in"].view(np.uint32).copy(), np.arange(8192, dtype=np.uint32))
+    assert np.array_equal(keys.view(np.float32), z["keys_out"])
+    assert np.array_equal(vals, np.arange(8191, -1, -1, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("n", [1, 31, 4095, 4096, 4097, 12289, 1_000_003])
+def test_sort_matches_stable_sort(ws, ctx, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    keys[: n // 3] &= 0x3ff                                   # heavy ties: stability
+    keys[n // 2: n // 2 + n // 8] = 0xffffffff                # real keys equal to the pad value
+    k, v = ws.sort_pairs_host(ctx, keys.copy(), np.arange(n, dtype=np.uint32))
+    o = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[o]) and np.array_equal(v, o.astype(np.uint32))
+
+
+@pytest.mark.parametrize("bits", [8, 13, 24])
+def test_sort_partial_key_bits(ws, ctx, bits):
+    rng = np.random.default_rng(bits)
+    n = 100_000
+    keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(np.uint32)
+    k, v = ws.sort_pairs_host(ctx, keys.copy(), np.arange(n, dtype=np.uint32), key_bits=bits)
+    o = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[o]) and np.array_equal(v, o.astype(np.uint32))
+
+
+def test_golden_frame(ws, orc, ctx):
+    """The committed golden vectors (tests/golden/oracle_small.npz)."""
+    z = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    cloud = ws.synth.make_cloud(int(z["n"]), int(z["seed"]))
+    pos, rot = ws.synth.orbit_camera(float(z["az"]))
+    W, H = int(z["W"]), int(z["H"])
+    r, pc, img, _ = _frame(ws, ctx, cloud, pos, rot, W, H)
+    assert np.array_equal(r.read_buffer(ws.BUF_SPLATS_2D), z["splats"])
+    assert np.array_equal(r.read_buffer(ws.BUF_DEPTH_KEYS), z["keys"])
+    assert np.array_equal(r.read_buffer(ws.BUF_SORTED_INDICES), z["order"])
+    assert r.stats()["num_pairs"] == int(z["pairs"])
+    assert np.abs(img - z["image"]).max() <= 4e-3 and np.abs(img - z["image"]).mean() <= 2e-5
+
+
+@pytest.mark.parametrize("n,W,H,az", [(5000, 320, 200, 30.0), (40000, 800, 600, 140.0), (40000, 1200, 799, 250.0), (777, 33, 17, 0.0)])
+def test_all_stages_small(ws, orc, ctx, n, W, H, az):
+    cloud = ws.synth.make_cloud(n, 100 + n)
+    pos, rot = ws.synth.orbit_camera(az)
+    _check_all_stages(ws, orc, ctx, cloud, pos, rot, W, H)
+
+
+def test_cfg1_full(ws, orc, ctx):
+    """BASELINE.json configs[0]: 100K Gaussians, 800x600, fixed camera."""
+    n, W, H, seed, _ = ws.synth.CONFIGS["cfg1"]
+    cloud = ws.synth.make_cloud(n, seed)
+    pos, rot = ws.synth.fixed_camera()
+    _check_all_stages(ws, orc, ctx, cloud, pos, rot, W, H)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_lower_sh_degree(ws, orc, ctx, deg):
+    cloud = ws.synth.make_cloud(20000, 5)
+    pos, rot = ws.synth.orbit_camera(80.0)
+    _check_all_stages(ws, orc, ctx, cloud, pos, rot, 400, 300, max_sh_deg=deg)
+
+
+def test_options_mip_kernel_scaling_walltime(ws, orc, ctx):
+    """§8(f) N4 options: mip-splatting compensation, kernel size, gaussian_scaling, walltime reveal."""
+    cloud = ws.synth.make_cloud(20000, 6)
+    pos, rot = ws.synth.orbit_camera(10.0)
+    _check_all_stages(ws, orc, ctx, cloud, pos, rot, 400, 300, mip_splatting=True, kernel_size=0.1)
+    _check_all_stages(ws, orc, ctx, cloud, pos, rot, 400, 300, gaussian_scaling=0.5)
+    _check_all_stages(ws, orc, ctx, cloud, pos, rot, 400, 300, walltime=0.6)       # partially revealed: NaN axes vanish
+
+
+def test_edge_cases(ws, orc, ctx):
+    import torch
+    pos, rot = ws.synth.fixed_camera()
+    # empty cloud
+    c0 = ws.synth.make_cloud(0, 1)
+    r, pc, img, _ = _frame(ws, ctx, c0, pos, rot, 64, 48, clear=(0.25, 0.5, 0.75, 1.0))
+    assert r.num_visible_points() == 0 and r.stats()["num_pairs"] == 0
+    assert np.allclose(img, (0.25, 0.5, 0.75, 1.0))
+    # everything culled (camera looks away)
+    c1 = ws.synth.make_cloud(3000, 2)
+    r, pc, img, _ = _frame(ws, ctx, c1, np.array([0, 0, 3], np.float32), rot, 64, 48)
+    assert r.num_visible_points() == 0 and np.count_nonzero(img) == 0
+    # one huge splat covering every tile + a few small ones
+    c2 = ws.synth.make_cloud(300, 3)
+    c2["gaussians"]["cov"][0] = np.array([4, 0.01, 0, 4, 0, 4], np.float16)
+    _check_all_stages(ws, orc, ctx, c2, pos, rot, 330, 250)
+
+
+def test_output_formats(ws, orc, ctx):
+    cloud = ws.synth.make_cloud(20000, 9)
+    pos, rot = ws.synth.orbit_camera(300.0)
+    W, H = 400, 300
+    clear = (0.1, 0.2, 0.3, 1.0)
+    _, _, f32, _ = _frame(ws, ctx, cloud, pos, rot, W, H, ws.FORMAT_RGBA32_FLOAT, clear)
+    _, _, f16, _ = _frame(ws, ctx, cloud, pos, rot, W, H, ws.FORMAT_RGBA16_FLOAT, clear)
+    _, _, u8, _ = _frame(ws, ctx, cloud, pos, rot, W, H, ws.FORMAT_RGBA8_UNORM, clear)
+    assert np.array_equal(f16, f32.astype(np.float16))
+    assert np.array_equal(u8, np.rint(np.clip(f32, 0, 1) * 255).astype(np.uint8))
+
+
+def test_render_to_host_and_reuse(ws, orc, ctx):
+    """render_to_host == render + copy; a renderer serves several clouds / viewports in a row
+    (sort buffers re-created when the point count changes, renderer.rs:200-211)."""
+    import torch
+    r = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA16_FLOAT, 3, False)
+    for n, W, H in ((3000, 160, 96), (9000, 320, 200), (3000, 160, 96)):
+        cloud = ws.synth.make_cloud(n, n)
+        pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+        pos, rot = ws.synth.orbit_camera(45.0)
+        fovx, fovy = ws.synth.fov_for_viewport(W, H)
+        args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
+        r.prepare(None, pc, args)
+        host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory()
+        r.render_to_host(host, pc)
+        dev = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
+        r.render(dev, pc)
+        torch.cuda.synchronize()
+        assert torch.equal(dev.cpu(), host)
+        ref = orc.render_frame(cloud, pos, rot, W, H, fovx, fovy)
+        assert np.abs(host.numpy().astype(np.float32) - ref["image"]).max() < 6e-3
+
+
+def test_errors(ws, ctx):
+    cloud = ws.synth.make_cloud(2000, 4)
+    pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+    r = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA32_FLOAT, 3, False)
+    import torch
+    t = torch.empty((48, 64, 4), device="cuda")
+    with pytest.raises(ws.WsError) as e:
+        r._viewport = (64, 48); r.render(t, pc)
+    assert e.value.status == ws.WS_ERR_NOT_PREPARED
+    rc = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA32_FLOAT, 3, True)
+    pos, rot = ws.synth.fixed_camera()
+    args = make_args(ws, cloud, pos, rot, 64, 48, *ws.synth.fov_for_viewport(64, 48))
+    with pytest.raises(ws.WsError) as e:
+        rc.prepare(None, pc, args)
+    assert e.value.status == ws.WS_ERR_MISMATCH
+    # pair overflow is reported, never silently dropped
+    r.set_pair_capacity(100)
+    r.prepare(None, pc, args)
+    st = r.stats(allow_overflow=True)
+    assert st["pair_overflow"] and st["num_pairs"] > 100
+    with pytest.raises(ws.WsError) as e:
+        r.stats()
+    assert e.value.status == ws.WS_ERR_PAIR_OVERFLOW
+
+
+def test_determinism(ws, ctx):
+    """Bit-reproducible frames (the reference's atomic slot order is not, preprocess.wgsl:262)."""
+    cloud = ws.synth.make_cloud(30000, 8)
+    pos, rot = ws.synth.orbit_camera(120.0)
+    imgs = [_frame(ws, ctx, cloud, pos, rot, 512, 288)[2] for _ in range(3)]
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])

@@ -1,0 +1,62 @@
+"""GPU tests at BASELINE.json's full sizes through size-independent properties (the oracle would
+take too long for a full-frame comparison at 6M on the test box; one oracle frame is compared)."""
+import numpy as np
+import pytest
+
+from helpers import make_args, make_generic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3"])
+def test_full_size_properties(ws, orc, ctx, cfg):
+    import torch
+    n, W, H, seed, _ = ws.synth.CONFIGS[cfg]
+    cloud = ws.synth.make_cloud(n, seed)
+    pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+    r = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA16_FLOAT, 3, False)
+    pos, rot = ws.synth.orbit_camera(40.0)
+    fovx, fovy = ws.synth.fov_for_viewport(W, H)
+    args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
+    r.prepare(None, pc, args)
+    target = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
+    r.render(target, pc)
+    torch.cuda.synchronize()
+    st = r.stats()
+    V, P = st["num_visible"], st["num_pairs"]
+    assert 0 < V <= n and P >= V * 0.5
+    # stage-1 parity on the full cloud against the (OpenMP) oracle: bit-exact
+    zn, zf = orc.fit_near_far(pos, cloud["aabb_min"], cloud["aabb_max"])
+    cam = orc.camera_uniform(pos, rot, fovx, fovy, zn, zf, W, H)
+    rs = orc.render_settings(cloud)
+    osplats, okeys, _ = orc.preprocess(cloud, cam, rs)
+    assert V == len(okeys)
+    assert np.array_equal(r.read_buffer(ws.BUF_SPLATS_2D), osplats)
+    # sortedness + permutation + stability of the depth sort
+    sk = r.read_buffer(ws.BUF_SORTED_KEYS); si = r.read_buffer(ws.BUF_SORTED_INDICES)
+    assert (np.diff(sk.astype(np.int64)) >= 0).all()
+    assert np.array_equal(np.sort(si), np.arange(V, dtype=np.uint32))
+    assert np.array_equal(okeys[si], sk)
+    ties = sk[1:] == sk[:-1]
+    assert (si[1:][ties] > si[:-1][ties]).all()
+    # pair list: sorted by tile, ranges partition it, per-tile depth order preserved
+    pt = r.read_buffer(ws.BUF_PAIR_TILES); ps = r.read_buffer(ws.BUF_PAIR_SLOTS)
+    assert len(pt) == P and (np.diff(pt.astype(np.int64)) >= 0).all()
+    rank = np.empty(V, np.int64); rank[si] = np.arange(V)
+    same = pt[1:] == pt[:-1]
+    assert (rank[ps[1:]][same] > rank[ps[:-1]][same]).all()
+    rects, Pref = orc.tile_rects(osplats, W, H)
+    assert P == Pref
+    rg = r.read_buffer(ws.BUF_TILE_RANGES)
+    assert (rg[:, 1] - rg[:, 0]).sum() == P
+    # image: finite, alpha in [0,1], idempotent re-render
+    img = target.cpu().numpy().astype(np.float32)
+    assert np.isfinite(img).all() and img[..., 3].min() >= 0 and img[..., 3].max() <= 1.0
+    t2 = torch.empty_like(target); r.render(t2, pc); torch.cuda.synchronize()
+    assert torch.equal(t2, target)
+    if cfg == "cfg2":
+        _, order = orc.sort_pairs(okeys, np.arange(V, dtype=np.uint32))
+        ref, sens = orc.composite(osplats, order, W, H, want_sens=True)
+        d = np.abs(img - ref).max(axis=2)
+        # f16 target: half an ulp of the f16 output on top of the f32 tolerance
+        assert (d <= 2e-3 + sens + 2.0 ** -11 * np.maximum(1.0, np.abs(ref).max(axis=2))).all()

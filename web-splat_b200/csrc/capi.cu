@@ -1,0 +1,787 @@
+// capi.cu -- host side of libwebsplat_b200: the C ABI declared in include/websplat_b200.h.
+//
+// Mirrors the host logic of the reference's render API for the hot path:
+//   PointCloud::new                     pointcloud.rs:99-199   -> ws_pointcloud_create
+//   GaussianRenderer::new               renderer.rs:33-123     -> ws_renderer_create
+//   GaussianRenderer::prepare           renderer.rs:191-248    -> ws_renderer_prepare
+//     CameraUniform setters             renderer.rs:321-343
+//     SplattingArgsUniform::from_args_and_pc   renderer.rs:620-651
+//     GPURSSorter::create_sort_stuff    gpu_rs.rs:141-175 (lazy, on point-count change)
+//   GaussianRenderer::render            renderer.rs:250-260    -> ws_renderer_render
+//   GaussianRenderer::num_visible_points renderer.rs:170-189   -> ws_renderer_num_visible_points
+//   GPUStopwatch                        utils.rs:26-134        -> ws_renderer_stats (CUDA events)
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point
+// that does work fails with WS_ERR_CUDA.
+#include "../../include/websplat_b200.h"
+#include "ws_device.cuh"
+#include "ws_kernels.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace ws;
+
+// ------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static ws_status fail_cuda(cudaError_t e, const char *what)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    g_last_error = buf;
+    return (e == cudaErrorMemoryAllocation) ? WS_ERR_OUT_OF_MEMORY : WS_ERR_CUDA;
+}
+static ws_status fail(ws_status s, const char *what)
+{
+    g_last_error = what;
+    return s;
+}
+#define CU(call)                                                         \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call);            \
+    } while (0)
+
+extern "C" const char *ws_status_string(ws_status s)
+{
+    switch (s) {
+    case WS_OK: return "ok";
+    case WS_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case WS_ERR_CUDA: return "CUDA error / no usable CUDA device";
+    case WS_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case WS_ERR_PAIR_OVERFLOW: return "(tile, splat) pair capacity exceeded";
+    case WS_ERR_NOT_PREPARED: return "render() called without prepare()";
+    case WS_ERR_UNSUPPORTED: return "unsupported";
+    case WS_ERR_MISMATCH: return "point cloud does not match the renderer specialisation";
+    default: return "unknown status";
+    }
+}
+extern "C" const char *ws_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *ws_version(void) { return "websplat_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------
+struct ws_context {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+};
+
+extern "C" ws_status ws_context_create(int cuda_device, ws_context **out)
+{
+    if (!out) return fail(WS_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (count <= 0) return fail(WS_ERR_CUDA, "no CUDA device");
+    if (cuda_device < 0 || cuda_device >= count) return fail(WS_ERR_INVALID_ARGUMENT, "cuda_device out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cuda_device));
+    if (prop.major != 10) return fail(WS_ERR_CUDA, "device is not compute capability 10.x (library is built for sm_100a only)");
+    CU(cudaSetDevice(cuda_device));
+    ws_context *c = new (std::nothrow) ws_context();
+    if (!c) return fail(WS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    c->device = cuda_device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major; c->cc_minor = prop.minor;
+    *out = c;
+    return WS_OK;
+}
+extern "C" void ws_context_destroy(ws_context *ctx) { delete ctx; }
+extern "C" int ws_context_device(const ws_context *ctx) { return ctx ? ctx->device : -1; }
+extern "C" int ws_context_sm_count(const ws_context *ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ------------------------------------------------------------------------------------
+// camera helpers
+extern "C" void ws_aabb_center(const ws_aabb *b, float out[3])
+{
+    for (int i = 0; i < 3; i++) out[i] = (b->min[i] + b->max[i]) * 0.5f;     // Point3::midpoint
+}
+extern "C" float ws_aabb_radius(const ws_aabb *b)
+{
+    float r2 = 0.f;
+    for (int i = 0; i < 3; i++) { float t = b->max[i] - b->min[i]; r2 = r2 + t * t; }
+    return sqrtf(r2) / 2.0f;                                                  // min.distance(max) / 2
+}
+extern "C" void ws_camera_fit_near_far(const float position[3], const ws_aabb *aabb, float *znear, float *zfar)
+{
+    // camera.rs:26-35
+    float c[3]; ws_aabb_center(aabb, c);
+    const float radius = ws_aabb_radius(aabb);
+    float d2 = 0.f;
+    for (int i = 0; i < 3; i++) { float t = c[i] - position[i]; d2 = d2 + t * t; }
+    const float distance = sqrtf(d2);
+    const float zf = distance + radius;
+    float zn = distance - radius;
+    const float lo = zf / 1000.f;
+    if (!(zn > lo)) zn = lo;
+    *zfar = zf; *znear = zn;
+}
+
+// CameraUniform::set_camera / set_viewport / set_focal, renderer.rs:136-141,321-343;
+// world2view camera.rs:207-214 (closed form [R | -R t]); build_proj camera.rs:216-234.
+static void build_camera_uniform(const ws_splatting_args *a, CameraUniform *u)
+{
+    const float s = a->cam_rotation_wxyz[0], x = a->cam_rotation_wxyz[1], y = a->cam_rotation_wxyz[2], z = a->cam_rotation_wxyz[3];
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx2 = x2 * x, xy2 = x2 * y, xz2 = x2 * z, yy2 = y2 * y, yz2 = y2 * z, zz2 = z2 * z;
+    const float sy2 = y2 * s, sz2 = z2 * s, sx2 = x2 * s;
+    float R[3][3];   // [column][row], cgmath Matrix3::from(Quaternion)
+    R[0][0] = 1.f - yy2 - zz2; R[0][1] = xy2 + sz2;       R[0][2] = xz2 - sy2;
+    R[1][0] = xy2 - sz2;       R[1][1] = 1.f - xx2 - zz2; R[1][2] = yz2 + sx2;
+    R[2][0] = xz2 + sy2;       R[2][1] = yz2 - sx2;       R[2][2] = 1.f - xx2 - yy2;
+    memset(u, 0, sizeof *u);
+    const float *t = a->cam_position;
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) {
+            u->view[c * 4 + r] = R[c][r];
+            u->view_inv[r * 4 + c] = R[c][r];
+        }
+    for (int r = 0; r < 3; r++) {
+        float acc = R[0][r] * t[0];
+        acc = acc + R[1][r] * t[1];
+        acc = acc + R[2][r] * t[2];
+        u->view[12 + r] = -acc;
+        u->view_inv[12 + r] = t[r];
+    }
+    u->view[15] = 1.f; u->view_inv[15] = 1.f;
+
+    const float znear = a->znear, zfar = a->zfar;
+    const float thy = tanf(a->fovy / 2.f), thx = tanf(a->fovx / 2.f);
+    const float top = thy * znear, bottom = -top, right = thx * znear, left = -right;
+    const float p00 = 2.0f * znear / (right - left);
+    const float p11 = 2.0f * znear / (top - bottom);
+    const float p02 = (right + left) / (right - left);
+    const float p12 = (top + bottom) / (top - bottom);
+    const float p22 = zfar / (zfar - znear);
+    const float p23 = -(zfar * znear) / (zfar - znear);
+    float P[16]; memset(P, 0, sizeof P);
+    P[0] = p00; P[5] = p11; P[8] = p02; P[9] = p12; P[10] = p22; P[11] = 1.f; P[14] = p23;
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) u->proj[c * 4 + r] = (r == 1) ? -P[c * 4 + r] : P[c * 4 + r];   // VIEWPORT_Y_FLIP * P
+    u->proj_inv[0] = 1.f / p00; u->proj_inv[5] = 1.f / p11;
+    u->proj_inv[12] = p02 / p00; u->proj_inv[13] = p12 / p11; u->proj_inv[14] = 1.f;
+    u->proj_inv[11] = 1.f / p23; u->proj_inv[15] = -p22 / p23;
+    u->viewport[0] = (float)a->viewport[0]; u->viewport[1] = (float)a->viewport[1];
+    u->focal[0] = (float)a->viewport[0] / (2.f * tanf(a->fovx * 0.5f));
+    u->focal[1] = (float)a->viewport[1] / (2.f * tanf(a->fovy * 0.5f));
+}
+
+// ------------------------------------------------------------------------------------
+struct ws_pointcloud {
+    ws_context *ctx;
+    uint32_t n, sh_deg;
+    bool compressed;
+    uint8_t *d_gaussians = nullptr, *d_sh = nullptr, *d_covars = nullptr;
+    Quant4 quant;
+    ws_aabb aabb;
+    float center[3];
+    int32_t has_up; float up[3];
+    int32_t has_mip, mip;
+    int32_t has_kernel; float kernel;
+    int32_t has_bg; float bg[3];
+};
+
+extern "C" void ws_pointcloud_destroy(ws_pointcloud *pc)
+{
+    if (!pc) return;
+    cudaSetDevice(pc->ctx->device);
+    cudaFree(pc->d_gaussians); cudaFree(pc->d_sh); cudaFree(pc->d_covars);
+    delete pc;
+}
+
+extern "C" ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_desc *d, ws_pointcloud **out)
+{
+    if (!ctx || !d || !out) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if (d->num_points > 0 && (!d->gaussians || !d->sh_coefs)) return fail(WS_ERR_INVALID_ARGUMENT, "gaussians / sh_coefs is NULL");
+    if (d->num_points >= (1ull << 30)) return fail(WS_ERR_UNSUPPORTED, "more than 2^30 - 1 points");
+    if (d->sh_deg > 3) return fail(WS_ERR_INVALID_ARGUMENT, "sh_deg > 3");
+    if (d->compressed && (!d->covars || !d->quantization)) return fail(WS_ERR_INVALID_ARGUMENT, "compressed cloud needs covars + quantization");
+    const uint32_t n = (uint32_t)d->num_points;
+    const size_t rec = d->compressed ? 24u : 28u;
+    if (!d->compressed && d->sh_bytes < (uint64_t)n * 96u) return fail(WS_ERR_INVALID_ARGUMENT, "sh_bytes < num_points * 96");
+    CU(cudaSetDevice(ctx->device));
+    ws_pointcloud *pc = new (std::nothrow) ws_pointcloud();
+    if (!pc) return fail(WS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    pc->ctx = ctx; pc->n = n; pc->sh_deg = d->sh_deg; pc->compressed = d->compressed != 0;
+    memset(&pc->quant, 0, sizeof pc->quant);
+    if (d->quantization) memcpy(&pc->quant, d->quantization, sizeof pc->quant);
+    pc->aabb = d->aabb;
+    memcpy(pc->center, d->center, sizeof pc->center);
+    pc->has_up = d->has_up; memcpy(pc->up, d->up, sizeof pc->up);
+    pc->has_mip = d->has_mip_splatting; pc->mip = d->mip_splatting;
+    pc->has_kernel = d->has_kernel_size; pc->kernel = d->kernel_size;
+    pc->has_bg = d->has_background; memcpy(pc->bg, d->background_color, sizeof pc->bg);
+
+    // records are padded to a whole 256-record partition so stage 1 can bulk-copy full partitions
+    const size_t padded = ((size_t)n + 255u) / 256u * 256u;
+    const size_t gbytes = (padded ? padded : 256u) * rec;
+    cudaError_t e;
+#define PC_CU(call) do { e = (call); if (e != cudaSuccess) { ws_status s__ = fail_cuda(e, #call); ws_pointcloud_destroy(pc); return s__; } } while (0)
+    PC_CU(cudaMalloc(&pc->d_gaussians, gbytes));
+    PC_CU(cudaMemset(pc->d_gaussians, 0, gbytes));
+    if (n) PC_CU(cudaMemcpy(pc->d_gaussians, d->gaussians, (size_t)n * rec, cudaMemcpyHostToDevice));
+    const size_t shb = d->sh_bytes ? (size_t)d->sh_bytes : 32u;
+    PC_CU(cudaMalloc(&pc->d_sh, shb + 32u));
+    if (d->sh_bytes) PC_CU(cudaMemcpy(pc->d_sh, d->sh_coefs, (size_t)d->sh_bytes, cudaMemcpyHostToDevice));
+    if (d->compressed) {
+        const size_t cb = (size_t)d->num_covars * 12u;
+        PC_CU(cudaMalloc(&pc->d_covars, cb ? cb : 16u));
+        if (cb) PC_CU(cudaMemcpy(pc->d_covars, d->covars, cb, cudaMemcpyHostToDevice));
+    }
+#undef PC_CU
+    *out = pc;
+    return WS_OK;
+}
+
+extern "C" uint32_t ws_pointcloud_num_points(const ws_pointcloud *pc) { return pc ? pc->n : 0; }
+extern "C" uint32_t ws_pointcloud_sh_deg(const ws_pointcloud *pc) { return pc ? pc->sh_deg : 0; }
+extern "C" int32_t ws_pointcloud_compressed(const ws_pointcloud *pc) { return pc ? (pc->compressed ? 1 : 0) : 0; }
+extern "C" ws_status ws_pointcloud_bbox(const ws_pointcloud *pc, ws_aabb *out)
+{
+    if (!pc || !out) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = pc->aabb; return WS_OK;
+}
+extern "C" ws_status ws_pointcloud_center(const ws_pointcloud *pc, float out[3])
+{
+    if (!pc || !out) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    memcpy(out, pc->center, 12); return WS_OK;
+}
+extern "C" int32_t ws_pointcloud_up(const ws_pointcloud *pc, float out[3])
+{
+    if (!pc) return 0;
+    if (pc->has_up && out) memcpy(out, pc->up, 12);
+    return pc->has_up;
+}
+extern "C" int32_t ws_pointcloud_mip_splatting(const ws_pointcloud *pc, int32_t *out)
+{
+    if (!pc) return 0;
+    if (pc->has_mip && out) *out = pc->mip;
+    return pc->has_mip;
+}
+extern "C" int32_t ws_pointcloud_dilation_kernel_size(const ws_pointcloud *pc, float *out)
+{
+    if (!pc) return 0;
+    if (pc->has_kernel && out) *out = pc->kernel;
+    return pc->has_kernel;
+}
+
+// ------------------------------------------------------------------------------------
+enum { EV_START = 0, EV_PRE, EV_DSORT, EV_BIN, EV_TSORT, EV_RANGES, EV_BLEND0, EV_BLEND1, EV_COUNT };
+enum { TK_PRE = 0, TK_BIN = 1, TK_DSORT = 2, TK_TSORT = 6 };
+
+struct ws_renderer {
+    ws_context *ctx;
+    ws_format format;
+    uint32_t sh_deg;
+    bool compressed;
+    bool timing = true;
+
+    // capacities
+    uint32_t n_cap = 0;            // points the sort buffers were created for (gpu_rs.rs:141)
+    uint64_t pair_cap_req = 0;     // user request (0 = auto)
+    uint32_t pair_cap = 0;
+    uint32_t tiles_cap = 0;
+
+    // device buffers
+    FrameUniforms *d_uniforms = nullptr;
+    uint8_t *d_scratch = nullptr; size_t scratch_bytes = 0;
+    FrameCounters *d_counters = nullptr;
+    uint32_t *d_hist_depth = nullptr, *d_hist_tile = nullptr;
+    uint32_t *d_scan_pre = nullptr, *d_scan_bin = nullptr;
+    uint32_t *d_status_depth = nullptr, *d_status_tile = nullptr;
+    uint32_t *d_splats = nullptr;
+    uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
+    uint2 *d_rects = nullptr;
+    uint32_t *d_ptiles[2] = {nullptr, nullptr}, *d_pslots[2] = {nullptr, nullptr};
+    uint2 *d_ranges = nullptr;
+    void *d_frame = nullptr; size_t frame_bytes = 0;
+
+    // launch geometry
+    int grid_pre = 0, grid_sort = 0, grid_bin = 0;
+
+    // frame state
+    FrameUniforms h_uniforms;
+    bool prepared = false;
+    bool rendered = false;
+    int depth_passes = 4, tile_passes = 2;
+    int depth_out = 0, tile_out = 0;       // which ping-pong buffer holds the sorted result
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool ev_ok = false;
+    cudaStream_t last_stream = nullptr;
+    uint32_t last_n = 0;
+};
+
+static void free_sort_stuff(ws_renderer *r)
+{
+    cudaFree(r->d_scratch); r->d_scratch = nullptr;
+    cudaFree(r->d_splats); r->d_splats = nullptr;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(r->d_keys[i]); r->d_keys[i] = nullptr;
+        cudaFree(r->d_vals[i]); r->d_vals[i] = nullptr;
+        cudaFree(r->d_ptiles[i]); r->d_ptiles[i] = nullptr;
+        cudaFree(r->d_pslots[i]); r->d_pslots[i] = nullptr;
+    }
+    cudaFree(r->d_rects); r->d_rects = nullptr;
+    r->n_cap = 0; r->pair_cap = 0;
+}
+
+extern "C" void ws_renderer_destroy(ws_renderer *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    free_sort_stuff(r);
+    cudaFree(r->d_uniforms); cudaFree(r->d_ranges); cudaFree(r->d_frame);
+    if (r->ev_ok) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(r->ev[i]);
+    delete r;
+}
+
+extern "C" ws_status ws_renderer_create(ws_context *ctx, ws_format fmt, uint32_t sh_deg, int32_t compressed, ws_renderer **out)
+{
+    if (!ctx || !out) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if ((int)fmt < 0 || (int)fmt > 2) return fail(WS_ERR_INVALID_ARGUMENT, "unknown color format");
+    if (sh_deg > 3) return fail(WS_ERR_INVALID_ARGUMENT, "sh_deg > 3");
+    CU(cudaSetDevice(ctx->device));
+    ws_renderer *r = new (std::nothrow) ws_renderer();
+    if (!r) return fail(WS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    r->ctx = ctx; r->format = fmt; r->sh_deg = sh_deg; r->compressed = compressed != 0;
+    cudaError_t e = cudaMalloc(&r->d_uniforms, sizeof(FrameUniforms));
+    if (e != cudaSuccess) { ws_status s = fail_cuda(e, "cudaMalloc uniforms"); ws_renderer_destroy(r); return s; }
+    for (int i = 0; i < EV_COUNT; i++) {
+        e = cudaEventCreate(&r->ev[i]);
+        if (e != cudaSuccess) { ws_status s = fail_cuda(e, "cudaEventCreate"); ws_renderer_destroy(r); return s; }
+    }
+    r->ev_ok = true;
+    // persistent grids: one wave of resident CTAs
+    r->grid_pre = ctx->sm_count * preprocess_blocks_per_sm(r->compressed);
+    r->grid_sort = ctx->sm_count * sort_pass_blocks_per_sm();
+    r->grid_bin = ctx->sm_count * binning_blocks_per_sm();
+    // 24-bit integer keys in the compressed shader (preprocess_compressed.wgsl:325): 3 digit passes
+    r->depth_passes = r->compressed ? 3 : 4;
+    memset(&r->h_uniforms, 0, sizeof r->h_uniforms);
+    *out = r;
+    return WS_OK;
+}
+extern "C" ws_format ws_renderer_color_format(const ws_renderer *r) { return r ? r->format : WS_FORMAT_RGBA8_UNORM; }
+
+extern "C" ws_status ws_renderer_set_pair_capacity(ws_renderer *r, uint64_t max_pairs)
+{
+    if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
+    if (max_pairs >= (1ull << 30)) return fail(WS_ERR_UNSUPPORTED, "pair capacity must be < 2^30");
+    r->pair_cap_req = max_pairs;
+    return WS_OK;
+}
+extern "C" ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled)
+{
+    if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
+    r->timing = enabled != 0;
+    return WS_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// GPURSSorter::create_sort_stuff analogue (gpu_rs.rs:141-175, renderer.rs:200-211)
+static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
+{
+    uint64_t want_pairs = r->pair_cap_req;
+    if (want_pairs == 0) {
+        want_pairs = (uint64_t)n * 8u;
+        if (want_pairs < (1u << 22)) want_pairs = 1u << 22;
+        if (want_pairs >= (1ull << 30)) want_pairs = (1ull << 30) - 1;
+    }
+    const uint32_t pair_cap = (uint32_t)want_pairs;
+    if (!(r->d_scratch && r->n_cap == n && r->pair_cap == pair_cap)) {
+        free_sort_stuff(r);
+        const size_t nn = n ? n : 1;
+        const size_t parts256 = (nn + 255) / 256;
+        const size_t sparts_n = (nn + SORT_PART - 1) / SORT_PART;
+        const size_t sparts_p = ((size_t)pair_cap + SORT_PART - 1) / SORT_PART;
+        size_t off = 0;
+        const size_t o_counters = off; off = align_up(off + sizeof(FrameCounters), 256);
+        const size_t o_hd = off; off = align_up(off + 4 * 256 * 4, 256);
+        const size_t o_ht = off; off = align_up(off + 4 * 256 * 4, 256);
+        const size_t o_sp = off; off = align_up(off + parts256 * 4, 256);
+        const size_t o_sb = off; off = align_up(off + parts256 * 4, 256);
+        const size_t o_sd = off; off = align_up(off + 4 * sparts_n * 256 * 4, 256);
+        const size_t o_st = off; off = align_up(off + 3 * sparts_p * 256 * 4, 256);
+        CU(cudaMalloc(&r->d_scratch, off));
+        r->scratch_bytes = off;
+        r->d_counters = reinterpret_cast<FrameCounters *>(r->d_scratch + o_counters);
+        r->d_hist_depth = reinterpret_cast<uint32_t *>(r->d_scratch + o_hd);
+        r->d_hist_tile = reinterpret_cast<uint32_t *>(r->d_scratch + o_ht);
+        r->d_scan_pre = reinterpret_cast<uint32_t *>(r->d_scratch + o_sp);
+        r->d_scan_bin = reinterpret_cast<uint32_t *>(r->d_scratch + o_sb);
+        r->d_status_depth = reinterpret_cast<uint32_t *>(r->d_scratch + o_sd);
+        r->d_status_tile = reinterpret_cast<uint32_t *>(r->d_scratch + o_st);
+        CU(cudaMalloc(&r->d_splats, nn * 20));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc(&r->d_keys[i], nn * 4));
+            CU(cudaMalloc(&r->d_vals[i], nn * 4));
+            CU(cudaMalloc(&r->d_ptiles[i], (size_t)pair_cap * 4));
+            CU(cudaMalloc(&r->d_pslots[i], (size_t)pair_cap * 4));
+        }
+        CU(cudaMalloc(&r->d_rects, nn * 8));
+        r->n_cap = n; r->pair_cap = pair_cap;
+    }
+    if (!r->d_ranges || r->tiles_cap < tiles) {
+        cudaFree(r->d_ranges); r->d_ranges = nullptr;
+        CU(cudaMalloc(&r->d_ranges, (size_t)(tiles ? tiles : 1) * 8));
+        r->tiles_cap = tiles;
+    }
+    return WS_OK;
+}
+
+// SplattingArgsUniform::from_args_and_pc, renderer.rs:620-651
+static void build_settings_uniform(const ws_splatting_args *a, const ws_pointcloud *pc, RenderSettings *s)
+{
+    memset(s, 0, sizeof *s);
+    s->gaussian_scaling = a->gaussian_scaling;
+    s->max_sh_deg = a->max_sh_deg;
+    s->mip_splatting = a->has_mip_splatting ? (a->mip_splatting ? 1u : 0u) : ((pc->has_mip && pc->mip) ? 1u : 0u);
+    s->kernel_size = a->has_kernel_size ? a->kernel_size : (pc->has_kernel ? pc->kernel : 0.3f /* DEFAULT_KERNEL_SIZE renderer.rs:601 */);
+    const ws_aabb *cb = a->has_clipping_box ? &a->clipping_box : &pc->aabb;
+    for (int i = 0; i < 3; i++) { s->clip_min[i] = cb->min[i]; s->clip_max[i] = cb->max[i]; }
+    s->walltime = a->walltime_secs;
+    for (int i = 0; i < 3; i++) s->center[i] = pc->center[i];         // args.scene_center is ignored (renderer.rs:644)
+    const float rad = ws_aabb_radius(&pc->aabb);
+    float ext = a->has_scene_extend ? a->scene_extend : rad;
+    if (!(ext > rad)) ext = rad;                                       // .max(pc.bbox().radius())
+    s->scene_extend = ext;
+}
+
+extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, void *cuda_stream)
+{
+    if (!r || !pc || !args) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (pc->compressed != r->compressed) return fail(WS_ERR_MISMATCH, "renderer/point cloud 'compressed' mismatch");
+    if (r->compressed && pc->sh_deg != r->sh_deg) return fail(WS_ERR_MISMATCH, "compressed cloud sh_deg differs from the renderer's");
+    if (args->viewport[0] == 0 || args->viewport[1] == 0) return fail(WS_ERR_INVALID_ARGUMENT, "empty viewport");
+    if (args->viewport[0] > 16384 || args->viewport[1] > 16384) return fail(WS_ERR_UNSUPPORTED, "viewport larger than 16384");
+    if (args->max_sh_deg > 3) return fail(WS_ERR_INVALID_ARGUMENT, "max_sh_deg > 3");
+    if (r->compressed && args->max_sh_deg > r->sh_deg) return fail(WS_ERR_INVALID_ARGUMENT, "max_sh_deg exceeds the compressed cloud's degree");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+
+    const uint32_t W = args->viewport[0], H = args->viewport[1];
+    const uint32_t tx = (W + TILE - 1) / TILE, ty = (H + TILE - 1) / TILE;
+    const uint32_t tiles = tx * ty;
+    r->prepared = false; r->rendered = false;
+    ws_status st = ensure_capacity(r, pc->n, tiles);
+    if (st != WS_OK) return st;
+
+    FrameUniforms &U = r->h_uniforms;
+    build_camera_uniform(args, &U.cam);
+    build_settings_uniform(args, pc, &U.rs);
+    U.quant = pc->quant;
+    U.width = W; U.height = H; U.tiles_x = tx; U.tiles_y = ty;
+    U.num_points = pc->n; U.file_sh_deg = pc->sh_deg; U.pair_capacity = r->pair_cap; U._pad0 = 0;
+    r->tile_passes = (tiles > 65536u) ? 3 : ((tiles > 256u) ? 2 : 1);
+
+    // pageable source: the runtime stages the 0.5 KB before returning, so h_uniforms may be reused
+    CU(cudaMemcpyAsync(r->d_uniforms, &U, sizeof U, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
+    CU(cudaMemsetAsync(r->d_ranges, 0, (size_t)tiles * 8, stream));
+
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
+    {   // ---- stage 1
+        PreprocessArgs a;
+        a.gaussians = pc->d_gaussians; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
+        a.uniforms = r->d_uniforms;
+        a.splats = r->d_splats; a.depth_keys = r->d_keys[0]; a.slot_vals = r->d_vals[0]; a.rects = r->d_rects;
+        a.scan_status = r->d_scan_pre; a.ticket = &r->d_counters->ticket[TK_PRE];
+        a.hist = r->d_hist_depth; a.counters = r->d_counters;
+        CU(launch_preprocess(a, r->compressed, r->grid_pre, stream));
+    }
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
+    {   // ---- stage 2a: depth passes on the V visible splats
+        const size_t sparts_n = ((size_t)(r->n_cap ? r->n_cap : 1) + SORT_PART - 1) / SORT_PART;
+        int src = 0;
+        for (int p = 0; p < r->depth_passes; p++) {
+            SortPassArgs a;
+            a.keys_in = r->d_keys[src]; a.vals_in = r->d_vals[src];
+            a.keys_out = r->d_keys[src ^ 1]; a.vals_out = r->d_vals[src ^ 1];
+            a.n_ptr = &r->d_counters->num_visible; a.n_cap = r->n_cap;
+            a.status = r->d_status_depth + (size_t)p * sparts_n * 256;
+            a.ticket = &r->d_counters->ticket[TK_DSORT + p];
+            a.hist = r->d_hist_depth + p * 256;
+            a.shift = 8u * (uint32_t)p;
+            a.err = &r->d_counters->error_flags;
+            CU(launch_sort_pass(a, r->grid_sort, stream));
+            src ^= 1;
+        }
+        r->depth_out = src;
+    }
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_DSORT], stream));
+    {   // ---- stage 2b: expand into (tile, slot) pairs in depth order
+        BinningArgs a;
+        a.sorted_slots = r->d_vals[r->depth_out]; a.rects = r->d_rects; a.uniforms = r->d_uniforms;
+        a.counters = r->d_counters; a.pair_tiles = r->d_ptiles[0]; a.pair_slots = r->d_pslots[0];
+        a.scan_status = r->d_scan_bin; a.ticket = &r->d_counters->ticket[TK_BIN]; a.hist = r->d_hist_tile;
+        CU(launch_binning(a, r->grid_bin, stream));
+    }
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_BIN], stream));
+    {   // ---- stage 2c: tile-id passes on the P pairs
+        const size_t sparts_p = ((size_t)r->pair_cap + SORT_PART - 1) / SORT_PART;
+        int src = 0;
+        for (int p = 0; p < r->tile_passes; p++) {
+            SortPassArgs a;
+            a.keys_in = r->d_ptiles[src]; a.vals_in = r->d_pslots[src];
+            a.keys_out = r->d_ptiles[src ^ 1]; a.vals_out = r->d_pslots[src ^ 1];
+            a.n_ptr = &r->d_counters->num_pairs; a.n_cap = r->pair_cap;
+            a.status = r->d_status_tile + (size_t)p * sparts_p * 256;
+            a.ticket = &r->d_counters->ticket[TK_TSORT + p];
+            a.hist = r->d_hist_tile + p * 256;
+            a.shift = 8u * (uint32_t)p;
+            a.err = &r->d_counters->error_flags;
+            CU(launch_sort_pass(a, r->grid_sort, stream));
+            src ^= 1;
+        }
+        r->tile_out = src;
+    }
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_TSORT], stream));
+    CU(launch_tile_ranges(r->d_ptiles[r->tile_out], r->d_counters, r->pair_cap, r->d_ranges, r->ctx->sm_count * 8, stream));
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_RANGES], stream));
+
+    r->prepared = true;
+    r->last_stream = stream;
+    r->last_n = pc->n;
+    return WS_OK;
+}
+
+static size_t bytes_per_pixel(ws_format f) { return f == WS_FORMAT_RGBA8_UNORM ? 4 : (f == WS_FORMAT_RGBA16_FLOAT ? 8 : 16); }
+
+extern "C" ws_status ws_renderer_render(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch,
+                                        const double clear[4], void *cuda_stream)
+{
+    if (!r || !pc || !dst) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!r->prepared) return fail(WS_ERR_NOT_PREPARED, "prepare() must precede render()");
+    const FrameUniforms &U = r->h_uniforms;
+    const size_t bpp = bytes_per_pixel(r->format);
+    if (row_pitch < (size_t)U.width * bpp || (row_pitch % bpp) != 0 || row_pitch > 0xffffffffu)
+        return fail(WS_ERR_INVALID_ARGUMENT, "row_pitch_bytes too small or not a multiple of the pixel size");
+    if (((uintptr_t)dst % bpp) != 0) return fail(WS_ERR_INVALID_ARGUMENT, "dst is not aligned to the pixel size");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    CompositeArgs a;
+    a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
+    a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
+    for (int i = 0; i < 4; i++) a.clear[i] = clear ? (float)clear[i] : 0.f;
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND0], stream));
+    CU(launch_composite(a, U.tiles_x, U.tiles_y, stream));
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND1], stream));
+    r->rendered = true;
+    r->last_stream = stream;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_render_to_host(ws_renderer *r, ws_pointcloud *pc, void *dst_host, size_t row_pitch,
+                                                const double clear[4], void *cuda_stream)
+{
+    if (!r || !pc || !dst_host) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!r->prepared) return fail(WS_ERR_NOT_PREPARED, "prepare() must precede render()");
+    const FrameUniforms &U = r->h_uniforms;
+    const size_t bpp = bytes_per_pixel(r->format);
+    const size_t tight = (size_t)U.width * bpp;
+    if (row_pitch < tight) return fail(WS_ERR_INVALID_ARGUMENT, "row_pitch_bytes too small");
+    const size_t need = tight * U.height;
+    CU(cudaSetDevice(r->ctx->device));
+    if (r->frame_bytes < need) {
+        cudaFree(r->d_frame); r->d_frame = nullptr; r->frame_bytes = 0;
+        CU(cudaMalloc(&r->d_frame, need));
+        r->frame_bytes = need;
+    }
+    ws_status st = ws_renderer_render(r, pc, r->d_frame, tight, clear, cuda_stream);
+    if (st != WS_OK) return st;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (row_pitch == tight) CU(cudaMemcpyAsync(dst_host, r->d_frame, need, cudaMemcpyDeviceToHost, stream));
+    else CU(cudaMemcpy2DAsync(dst_host, row_pitch, r->d_frame, tight, tight, U.height, cudaMemcpyDeviceToHost, stream));
+    return WS_OK;
+}
+
+static ws_status read_counters(ws_renderer *r, FrameCounters *c)
+{
+    CU(cudaSetDevice(r->ctx->device));
+    CU(cudaStreamSynchronize(r->last_stream));
+    CU(cudaMemcpy(c, r->d_counters, sizeof *c, cudaMemcpyDeviceToHost));
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_num_visible_points(ws_renderer *r, uint32_t *out)
+{
+    if (!r || !out) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!r->prepared) return fail(WS_ERR_NOT_PREPARED, "no frame prepared");
+    FrameCounters c;
+    ws_status st = read_counters(r, &c);
+    if (st != WS_OK) return st;
+    *out = c.num_visible;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
+{
+    if (!r || !s) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!r->prepared) return fail(WS_ERR_NOT_PREPARED, "no frame prepared");
+    memset(s, 0, sizeof *s);
+    FrameCounters c;
+    ws_status st = read_counters(r, &c);
+    if (st != WS_OK) return st;
+    const FrameUniforms &U = r->h_uniforms;
+    s->num_points = r->last_n; s->num_visible = c.num_visible; s->num_pairs = c.num_pairs;
+    s->pair_capacity = r->pair_cap; s->num_tiles = U.tiles_x * U.tiles_y; s->width = U.width; s->height = U.height;
+    if (r->timing) {
+        auto el = [&](int a, int b) { float ms = 0.f; return (cudaEventElapsedTime(&ms, r->ev[a], r->ev[b]) == cudaSuccess) ? ms : 0.f; };
+        s->ms_preprocess = el(EV_START, EV_PRE);
+        s->ms_depth_sort = el(EV_PRE, EV_DSORT);
+        s->ms_binning = el(EV_DSORT, EV_BIN);
+        s->ms_tile_sort = el(EV_BIN, EV_TSORT);
+        s->ms_ranges = el(EV_TSORT, EV_RANGES);
+        s->ms_sort = el(EV_PRE, EV_RANGES);
+        if (r->rendered) s->ms_blend = el(EV_BLEND0, EV_BLEND1);
+        cudaGetLastError();
+    }
+    const uint64_t N = r->last_n, V = c.num_visible;
+    const uint64_t P = c.num_pairs < r->pair_cap ? c.num_pairs : r->pair_cap;
+    const uint64_t T = s->num_tiles;
+    const uint64_t rec = r->compressed ? 24 : 28;
+    const uint64_t ncoef = (uint64_t)(U.rs.max_sh_deg + 1) * (U.rs.max_sh_deg + 1);
+    const uint64_t shb = r->compressed ? (12 + 3 * ncoef) : (U.rs.max_sh_deg >= 3 ? 96 : (U.rs.max_sh_deg == 2 ? 64 : 32));
+    s->bytes_preprocess = N * rec + V * shb + V * (20 + 4 + 4 + 8);
+    s->bytes_sort = (uint64_t)r->depth_passes * V * 16 + V * 12 + P * 8 + (uint64_t)r->tile_passes * P * 16 + P * 4 + T * 8;
+    s->bytes_blend = P * 24 + T * 8 + (uint64_t)U.width * U.height * bytes_per_pixel(r->format);
+    if (c.error_flags) return fail(WS_ERR_CUDA, "internal: decoupled look-back watchdog fired");
+    if (c.pair_overflow) return fail(WS_ERR_PAIR_OVERFLOW, "pair capacity exceeded; raise it with ws_renderer_set_pair_capacity");
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_read_buffer(ws_renderer *r, ws_buffer_id which, void *dst, size_t dst_bytes, size_t *written)
+{
+    if (!r || !dst) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!r->prepared) return fail(WS_ERR_NOT_PREPARED, "no frame prepared");
+    FrameCounters c;
+    ws_status st = read_counters(r, &c);
+    if (st != WS_OK) return st;
+    const size_t V = c.num_visible;
+    const size_t P = c.num_pairs < r->pair_cap ? c.num_pairs : r->pair_cap;
+    const size_t T = (size_t)r->h_uniforms.tiles_x * r->h_uniforms.tiles_y;
+    const void *src = nullptr; size_t bytes = 0;
+    switch (which) {
+    case WS_BUF_SPLATS_2D: src = r->d_splats; bytes = V * 20; break;
+    case WS_BUF_DEPTH_KEYS:
+        // slot-order keys live in keys[0] only until the first pass overwrote it on the way back;
+        // with an even pass count keys[0] holds the SORTED keys, so slot order is re-derived below
+        src = nullptr; bytes = V * 4; break;
+    case WS_BUF_SORTED_INDICES: src = r->d_vals[r->depth_out]; bytes = V * 4; break;
+    case WS_BUF_SORTED_KEYS: src = r->d_keys[r->depth_out]; bytes = V * 4; break;
+    case WS_BUF_TILE_RECTS: src = r->d_rects; bytes = V * 8; break;
+    case WS_BUF_PAIR_TILES: src = r->d_ptiles[r->tile_out]; bytes = P * 4; break;
+    case WS_BUF_PAIR_SLOTS: src = r->d_pslots[r->tile_out]; bytes = P * 4; break;
+    case WS_BUF_TILE_RANGES: src = r->d_ranges; bytes = T * 8; break;
+    default: return fail(WS_ERR_INVALID_ARGUMENT, "unknown buffer id");
+    }
+    if (written) *written = bytes;
+    if (dst_bytes < bytes) return fail(WS_ERR_INVALID_ARGUMENT, "destination too small");
+    if (which == WS_BUF_DEPTH_KEYS) {
+        // un-permute on the host: key_of_slot[sorted_idx[i]] = sorted_key[i]
+        std::vector<uint32_t> sk(V), si(V);
+        if (V) {
+            CU(cudaMemcpy(sk.data(), r->d_keys[r->depth_out], V * 4, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(si.data(), r->d_vals[r->depth_out], V * 4, cudaMemcpyDeviceToHost));
+        }
+        uint32_t *o = static_cast<uint32_t *>(dst);
+        for (size_t i = 0; i < V; i++) if (si[i] < V) o[si[i]] = sk[i];
+        return WS_OK;
+    }
+    if (bytes) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_camera_uniform(const ws_renderer *r, float out68[68])
+{
+    if (!r || !out68) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    memcpy(out68, &r->h_uniforms.cam, sizeof(CameraUniform));
+    return WS_OK;
+}
+extern "C" ws_status ws_renderer_settings_uniform(const ws_renderer *r, void *out80)
+{
+    if (!r || !out80) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    memcpy(out80, &r->h_uniforms.rs, sizeof(RenderSettings));
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// The sort on its own (GPURSSorter::record_sort, gpu_rs.rs:865-873; KAT gpu_rs.rs:295-331)
+extern "C" ws_status ws_sort_pairs_u32(ws_context *ctx, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t key_bits, void *cuda_stream)
+{
+    if (!ctx) return fail(WS_ERR_INVALID_ARGUMENT, "NULL context");
+    if (key_bits < 1 || key_bits > 32) return fail(WS_ERR_INVALID_ARGUMENT, "key_bits must be in [1,32]");
+    if (n >= (1u << 30)) return fail(WS_ERR_UNSUPPORTED, "n must be < 2^30");
+    if (n == 0) return WS_OK;
+    if (!keys || !vals) return fail(WS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(ctx->device));
+    const int passes = (int)((key_bits + 7) / 8);
+    const size_t sparts = ((size_t)n + SORT_PART - 1) / SORT_PART;
+    // scratch: [n u32][tickets 4][hist 4*256][status passes*sparts*256] + ping-pong buffers
+    const size_t scratch_words = 8 + 4 * 256 + (size_t)passes * sparts * 256;
+    uint32_t *scratch = nullptr, *k2 = nullptr, *v2 = nullptr;
+    CU(cudaMalloc(&scratch, scratch_words * 4));
+    cudaError_t e = cudaMalloc(&k2, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&v2, (size_t)n * 4);
+    if (e != cudaSuccess) { cudaFree(scratch); cudaFree(k2); cudaFree(v2); return fail_cuda(e, "cudaMalloc sort temp"); }
+    ws_status st = WS_OK;
+    do {
+        e = cudaMemsetAsync(scratch, 0, scratch_words * 4, stream); if (e != cudaSuccess) break;
+        e = cudaMemcpyAsync(scratch, &n, 4, cudaMemcpyHostToDevice, stream); if (e != cudaSuccess) break;
+        uint32_t *n_ptr = scratch, *tickets = scratch + 4, *hist = scratch + 8, *status = scratch + 8 + 4 * 256;
+        e = launch_sort_histogram(keys, n_ptr, n, hist, passes, ctx->sm_count * 4, stream); if (e != cudaSuccess) break;
+        const int grid = ctx->sm_count * sort_pass_blocks_per_sm();
+        uint32_t *kb[2] = {keys, k2}, *vb[2] = {vals, v2};
+        int src = 0;
+        for (int p = 0; p < passes && e == cudaSuccess; p++) {
+            SortPassArgs a;
+            a.keys_in = kb[src]; a.vals_in = vb[src]; a.keys_out = kb[src ^ 1]; a.vals_out = vb[src ^ 1];
+            a.n_ptr = n_ptr; a.n_cap = n; a.status = status + (size_t)p * sparts * 256; a.ticket = tickets + p;
+            a.hist = hist + p * 256; a.shift = 8u * (uint32_t)p; a.err = nullptr;
+            e = launch_sort_pass(a, grid, stream);
+            src ^= 1;
+        }
+        if (e != cudaSuccess) break;
+        if (src == 1) {   // odd pass count: bring the result home
+            e = cudaMemcpyAsync(keys, k2, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) break;
+            e = cudaMemcpyAsync(vals, v2, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) break;
+        }
+        e = cudaStreamSynchronize(stream);   // temp buffers are freed below
+    } while (0);
+    if (e != cudaSuccess) st = fail_cuda(e, "ws_sort_pairs_u32");
+    cudaFree(scratch); cudaFree(k2); cudaFree(v2);
+    return st;
+}
+
+extern "C" ws_status ws_sort_pairs_u32_host(ws_context *ctx, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t key_bits)
+{
+    if (!ctx) return fail(WS_ERR_INVALID_ARGUMENT, "NULL context");
+    if (n == 0) return WS_OK;
+    if (!keys || !vals) return fail(WS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    uint32_t *dk = nullptr, *dv = nullptr;
+    CU(cudaMalloc(&dk, (size_t)n * 4));
+    cudaError_t e = cudaMalloc(&dv, (size_t)n * 4);
+    if (e != cudaSuccess) { cudaFree(dk); return fail_cuda(e, "cudaMalloc"); }
+    ws_status st = WS_OK;
+    e = cudaMemcpy(dk, keys, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dv, vals, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) st = fail_cuda(e, "cudaMemcpy H2D");
+    if (st == WS_OK) st = ws_sort_pairs_u32(ctx, dk, dv, n, key_bits, nullptr);
+    if (st == WS_OK) {
+        e = cudaMemcpy(keys, dk, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(vals, dv, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) st = fail_cuda(e, "cudaMemcpy D2H");
+    }
+    cudaFree(dk); cudaFree(dv);
+    return st;
+}

@@ -1,0 +1,155 @@
+// ws_device.cuh -- shared device-side definitions for the sm_100a splat render path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace ws {
+
+// ---- uniforms: byte-identical to the reference's uniform buffers -------------
+struct CameraUniform {      // renderer.rs:290-306 / preprocess.wgsl:26-34, 272 B
+    float view[16];         // column-major m[c*4+r]
+    float view_inv[16];
+    float proj[16];         // VIEWPORT_Y_FLIP * proj
+    float proj_inv[16];
+    float viewport[2];
+    float focal[2];
+};
+struct RenderSettings {     // renderer.rs:604-619 / preprocess.wgsl:77-87, 80 B
+    float clip_min[4];
+    float clip_max[4];
+    float gaussian_scaling;
+    uint32_t max_sh_deg;
+    uint32_t mip_splatting;
+    float kernel_size;
+    float walltime;
+    float scene_extend;
+    uint32_t _pad[2];
+    float center[4];
+};
+struct Quant { int32_t zero_point; float scale; uint32_t _pad[2]; };
+struct Quant4 { Quant color_dc, color_rest, opacity, scaling_factor; };
+
+struct FrameUniforms {      // one device-resident block per renderer, rewritten per frame
+    CameraUniform cam;
+    RenderSettings rs;
+    Quant4 quant;
+    uint32_t width, height, tiles_x, tiles_y;
+    uint32_t num_points, file_sh_deg, pair_capacity, _pad0;
+};
+
+// ---- per-frame device counters (zeroed by one memset per frame) ---------------
+struct FrameCounters {
+    uint32_t num_visible;       // V
+    uint32_t num_pairs;         // P (pairs needed, may exceed capacity)
+    uint32_t pair_overflow;     // 1 if P > capacity
+    uint32_t error_flags;       // bit 0: a look-back spin exceeded SPIN_LIMIT (never expected)
+    uint32_t ticket[12];        // dynamic partition tickets: [0] preprocess, [1] binning, [2..] sort passes
+};
+
+constexpr int TILE = 16;                    // 16x16 pixel tiles
+constexpr float CUTOFF = 2.3539888583335364f;               // gaussian.wgsl:2
+constexpr float TWO_CUTOFF = 4.707977716667073f;            // discard threshold, gaussian.wgsl:62
+constexpr float FOOTPRINT_R = 2.1697876f;                   // sqrt(2*CUTOFF)
+constexpr float RECT_PAD = 0.05f;                           // px, conservative pad of the tile rect
+
+// ---- decoupled look-back status words: [31:30] flag, [29:0] value -------------
+constexpr uint32_t LB_FLAG_SHIFT = 30;
+constexpr uint32_t LB_VALUE_MASK = 0x3fffffffu;
+constexpr uint32_t LB_INVALID = 0u;
+constexpr uint32_t LB_AGGREGATE = 1u << LB_FLAG_SHIFT;
+constexpr uint32_t LB_PREFIX = 2u << LB_FLAG_SHIFT;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;    // watchdog: a stuck look-back flags an error instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Warp-parallel decoupled look-back over a chain of single-word statuses.
+// Called by one full warp.  status[part] must already hold this partition's
+// AGGREGATE (or nothing yet: the caller publishes).  Returns the exclusive prefix
+// (sum of all partitions < part).  Each status word carries its own flag, so
+// relaxed accesses suffice (no separate payload to order against).
+__device__ __forceinline__ uint32_t lookback_warp(const uint32_t *status, uint32_t part, uint32_t *err)
+{
+    uint32_t spins = 0;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t excl = 0;
+    int64_t base = (int64_t)part - 1;          // window covers [base-31, base]
+    while (base >= 0) {
+        int64_t p = base - (int64_t)lane;
+        uint32_t s;
+        // spin until every lane's predecessor in the window (up to the first PREFIX) is valid
+        for (;;) {
+            s = (p >= 0) ? ld_relaxed(status + p) : LB_PREFIX;   // before partition 0: prefix 0
+            unsigned pref = __ballot_sync(0xffffffffu, (s >> LB_FLAG_SHIFT) == 2u);
+            unsigned inval = __ballot_sync(0xffffffffu, (s >> LB_FLAG_SHIFT) == 0u);
+            unsigned upto = pref ? ((pref & (0u - pref)) << 1) - 1u : 0xffffffffu;   // lanes <= first prefix lane
+            if ((inval & upto) == 0u) {
+                uint32_t v = ((1u << lane) & upto) ? (s & LB_VALUE_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (pref) return excl;
+                break;
+            }
+            if (++spins > SPIN_LIMIT) {
+                if (lane == 0 && err) atomicOr(err, 1u);
+                return excl;
+            }
+        }
+        base -= 32;
+    }
+    return excl;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, UBLKCP) ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; bytes multiple of 16, both addresses 16-B aligned
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace ws

@@ -1,0 +1,83 @@
+// ws_kernels.h -- host-visible launchers of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ws {
+
+struct FrameUniforms;
+struct FrameCounters;
+
+// ---- stage 1 -----------------------------------------------------------------
+struct PreprocessArgs {
+    const uint8_t *gaussians;     // N x 28 B (raw) / 24 B (compressed), padded to a multiple of 256 records
+    const uint8_t *sh_coefs;      // raw: N x 96 B; compressed: i8 entries
+    const uint8_t *covars;        // compressed only: 12 B per entry
+    const FrameUniforms *uniforms;
+    uint32_t *splats;             // out: V x 5 u32 (20-B Splat)
+    uint32_t *depth_keys;         // out: V
+    uint32_t *slot_vals;          // out: V (iota payload)
+    uint2 *rects;                 // out: V x {x0 | y0<<16, w | h<<16}
+    uint32_t *scan_status;        // ceil(N/256) look-back words (zeroed per frame)
+    uint32_t *ticket;             // zeroed per frame
+    uint32_t *hist;               // 4 x 256 depth-key digit histograms (zeroed per frame)
+    FrameCounters *counters;
+};
+cudaError_t launch_preprocess(const PreprocessArgs &a, bool compressed, int grid, cudaStream_t stream);
+int preprocess_blocks_per_sm(bool compressed);
+
+// ---- onesweep radix sort of (u32 key, u32 value) pairs ---------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_PART = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per partition
+
+struct SortPassArgs {
+    const uint32_t *keys_in, *vals_in;
+    uint32_t *keys_out, *vals_out;
+    const uint32_t *n_ptr;        // device: number of pairs (clamped to n_cap)
+    uint32_t n_cap;
+    uint32_t *status;             // [ceil(n_cap/4096)][256] look-back words, zeroed before the pass
+    uint32_t *ticket;             // zeroed before the pass
+    const uint32_t *hist;         // 256 digit counts of this pass (over the first min(*n_ptr,n_cap) keys)
+    uint32_t shift;               // digit = (key >> shift) & 255
+    uint32_t *err;                // optional error word (bit 0: look-back watchdog)
+};
+cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t stream);
+int sort_pass_blocks_per_sm();
+// digit histograms of up to 4 passes (shift 0,8,16,24) in one sweep over the keys; hist zeroed by caller
+cudaError_t launch_sort_histogram(const uint32_t *keys, const uint32_t *n_ptr, uint32_t n_cap,
+                                  uint32_t *hist /*4x256*/, int passes, int grid, cudaStream_t stream);
+
+// ---- tile binning: expand depth-sorted splats into (tile, slot) pairs ----------------
+struct BinningArgs {
+    const uint32_t *sorted_slots; // V: payload after the depth sort
+    const uint2 *rects;           // per slot
+    const FrameUniforms *uniforms;
+    FrameCounters *counters;      // reads num_visible, writes num_pairs / pair_overflow
+    uint32_t *pair_tiles;         // out: P tile ids
+    uint32_t *pair_slots;         // out: P slots
+    uint32_t *scan_status;        // ceil(N/256) look-back words (zeroed per frame)
+    uint32_t *ticket;
+    uint32_t *hist;               // 4 x 256 tile-id digit histograms (zeroed per frame)
+};
+cudaError_t launch_binning(const BinningArgs &a, int grid, cudaStream_t stream);
+int binning_blocks_per_sm();
+
+// per-tile [begin,end) over the sorted pair list; ranges must be zeroed by the caller
+cudaError_t launch_tile_ranges(const uint32_t *pair_tiles, const FrameCounters *counters, uint32_t pair_cap,
+                               uint2 *ranges, int grid, cudaStream_t stream);
+
+// ---- stage 3 -----------------------------------------------------------------------
+struct CompositeArgs {
+    const uint32_t *splats;       // V x 5 u32
+    const uint32_t *pair_slots;   // sorted
+    const uint2 *ranges;          // T
+    const FrameUniforms *uniforms;
+    void *dst;                    // device frame
+    uint32_t row_pitch;           // bytes
+    int format;                   // ws_format
+    float clear[4];
+};
+cudaError_t launch_composite(const CompositeArgs &a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream);
+
+}  // namespace ws
