@@ -7,7 +7,7 @@
 //     b = min(0.99, exp(-a) * alpha);        dst = (rgb*b, b) + dst * (1 - b).
 // Here one CTA owns one 16x16 tile and walks the tile's slice of the sorted pair list from
 // its END (nearest splat) to its begin, accumulating C += rgb*b*T, T *= (1-b): the same sum,
-// associated front-to-back, which allows the early-out once T < 1e-4.
+// associated front-to-back, which allows the early-out once T < 2^-16.
 //
 //  * each warp owns an 8x4 pixel block; splats are staged 256 at a time into shared memory
 //    (decoded from the 20-B f16 record once per tile, not once per pixel);
@@ -26,7 +26,7 @@ namespace {
 
 constexpr int CB_THREADS = 256;
 constexpr int CB_BATCH = 256;
-constexpr float T_EPS = 1e-4f;
+constexpr float T_EPS = 1.52587890625e-5f;   // 2^-16: early-out once the remaining transmittance cannot move the result by more
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float SQRT_LOG2E = 1.2011224087864498f;
 
