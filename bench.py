@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "frames/sec"
-KERNELS_PER_FRAME_FIXED = 1 + 1 + 1 + 1     # preprocess, binning, tile ranges, composite (+ sort passes)
+KERNELS_PER_FRAME_FIXED = 1 + 1 + 1         # preprocess, binning, composite (+ onesweep passes; tile ranges are fused into the last pass)
 
 
 def measured_peaks():
@@ -49,40 +49,53 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe), sampled through
+    NVML every 10 ms (the nvidia-smi CLI takes ~100 ms per query, longer than a whole timed region)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxclk = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
 
     def run(self):
+        nv = self.nv
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if nv is not None:
+                    clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                    self.rows.append((float(clk), int(rs), int(util)))
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    c = [float(x) for x in out.strip().split(",")]
+                    self.maxclk = c[1]
+                    self.rows.append((c[0], 0, 100))
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.01)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(k for k, b in bits.items() if any(r[1] & b for r in self.rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(getattr(self, "maxclk", 0) or 0) or None,
+                "reasons": reasons, "samples": len(sm)}
 
 
 def make_workload(name):
@@ -263,7 +276,6 @@ def run_ours(args):
         "depth_sort_pass": {"ms": acc["ms_depth_sort"] / depth_passes, "bytes": V * 16, "launches": depth_passes},
         "binning": {"ms": acc["ms_binning"], "bytes": V * 12 + P * 8},
         "tile_sort_pass": {"ms": acc["ms_tile_sort"] / tile_passes, "bytes": P * 16, "launches": tile_passes},
-        "tile_ranges": {"ms": acc["ms_ranges"], "bytes": P * 4 + T * 8},
         "composite": {"ms": acc["ms_blend"], "bytes": acc["bytes_blend"]},
     }
     for kv in kernels.values():
@@ -299,7 +311,7 @@ def run_ours(args):
                    "N": N, "V_mean": V, "P_mean": P, "tiles": T},
         "ms_per_frame": {"preprocess": acc["ms_preprocess"], "sort": acc["ms_sort"], "blend": acc["ms_blend"],
                          "depth_sort": acc["ms_depth_sort"], "binning": acc["ms_binning"],
-                         "tile_sort": acc["ms_tile_sort"], "tile_ranges": acc["ms_ranges"]},
+                         "tile_sort": acc["ms_tile_sort"]},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 448, "d2h_bytes_per_step": W * H * 8,
                 "checksum": checksum},
@@ -321,7 +333,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 36 if args.impl == "ours" else 10     # ~5.5 s per cfg3 frame on 8 host cores
+        args.steps = 360 if args.impl == "ours" else 10    # 10 orbits (~1 s of GPU time) / ~2-5 s per CPU frame
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

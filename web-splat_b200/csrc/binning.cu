@@ -6,9 +6,25 @@
 // is a per-SPLAT property, so its four digit passes run on the V visible splats BEFORE they
 // are expanded into P >= V (tile, splat) pairs.  This kernel does the expansion: it walks
 // the splats in depth order, turns each tile rectangle into its (tile id, slot) pairs at
-// offsets given by a single-pass decoupled look-back scan, and counts the tile-id digits
-// for the two onesweep passes that follow.  The result after those passes is bit-identical
+// offsets given by a scan of the per-partition pair counts, and counts the tile-id digits
+// for the onesweep passes that follow.  The result after those passes is bit-identical
 // to sorting P 64-bit (tile|depth) keys with (tile, depth, slot) order, at ~1/3 of the traffic.
+//
+// Three launches, none with an inter-CTA dependency (a single-pass chained scan was measured
+// first, profiles/r01*: at ~900 pairs per partition every partition paid ~11 us of serialised
+// ticket / gather / look-back round trips and the kernel ran at 8 % of the HBM roofline):
+//   COUNT   pairs per 1024-splat partition (slot load + rectangle gather, 4 per thread in flight);
+//   SCAN    one CTA: exclusive scan of the partition totals, P, overflow flag;
+//   EXPAND  load-balanced over PAIRS, not splats: every splat with at least one tile drops a
+//           marker (its index) at the block-local offset of its first pair, a prefix-max over
+//           the positions (warp shuffles, 8 positions per thread) tells every output position
+//           which splat owns it, and the thread derives (tile x, tile y) from the position with
+//           one multiply-high (magic reciprocal of the rectangle width).  Threads emit
+//           consecutive pairs straight to global memory, perfectly coalesced, however uneven
+//           the rectangles are (a screen-filling splat simply owns many consecutive positions).
+// The digit histogram uses plain shared-memory atomicAdd (no return value): measured at
+// 118-135 G warp-ops/s on B200 whatever the address spread, 25x a MATCH.ANY-aggregated update
+// (profiles/microbench/rank_primitives.cu).
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
@@ -18,46 +34,133 @@ namespace {
 
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_WARPS = BIN_THREADS / 32;
+constexpr int BIN_SPT = 4;                            // splats per thread
+constexpr int BIN_PART = BIN_THREADS * BIN_SPT;       // 1024 splats per partition
+constexpr int BIN_ROUNDS = 8;                         // output positions per thread and chunk
+constexpr int BIN_CAP = BIN_THREADS * BIN_ROUNDS;     // 2048 pairs per chunk
+constexpr int BIN_NDIG = 3;
 
-__global__ void __launch_bounds__(BIN_THREADS, 4)
-binning_kernel(BinningArgs a)
+struct SplatRects { uint32_t slot[BIN_SPT], xy[BIN_SPT], w[BIN_SPT], cnt[BIN_SPT]; };
+
+// slots + rectangles of the BIN_SPT consecutive depth-sorted splats of one thread
+__device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first, uint32_t V, SplatRects &r)
 {
-    __shared__ uint32_t s_incl[BIN_THREADS];      // inclusive scan of pair counts in the partition
-    __shared__ uint32_t s_xy[BIN_THREADS];        // x0 | y0 << 16
-    __shared__ uint32_t s_w[BIN_THREADS];         // rect width
-    __shared__ uint32_t s_slot[BIN_THREADS];
-    __shared__ uint32_t s_hist[4 * 256];
+    if (first + BIN_SPT <= V) {
+        const uint4 s4 = *reinterpret_cast<const uint4 *>(a.sorted_slots + first);
+        r.slot[0] = s4.x; r.slot[1] = s4.y; r.slot[2] = s4.z; r.slot[3] = s4.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < BIN_SPT; j++) r.slot[j] = (first + j < V) ? a.sorted_slots[first + j] : 0xffffffffu;
+    }
+    uint2 rc[BIN_SPT];
+#pragma unroll
+    for (int j = 0; j < BIN_SPT; j++) rc[j] = (r.slot[j] != 0xffffffffu) ? __ldg(a.rects + r.slot[j]) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int j = 0; j < BIN_SPT; j++) {
+        r.xy[j] = rc[j].x;
+        r.w[j] = rc[j].y & 0xffffu;
+        r.cnt[j] = r.w[j] * (rc[j].y >> 16);
+    }
+}
+
+// ---- (1) COUNT ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_count_kernel(BinningArgs a)
+{
+    __shared__ uint32_t s_red[BIN_WARPS];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t V = a.counters->num_visible;
+    const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
+    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
+        SplatRects r;
+        load_rects(a, part * BIN_PART + tid * BIN_SPT, V, r);
+        uint32_t c = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) s_red[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int k = 0; k < BIN_WARPS; k++) t += s_red[k];
+            a.part_counts[part] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- (2) SCAN: exclusive scan of up to 2^20 partition totals by one CTA --------------------------
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(BinningArgs a)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_total;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t V = a.counters->num_visible;
+    const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < nparts; b += 1024u) {
+        const uint32_t i = b + tid;
+        const uint32_t c = (i < nparts) ? a.part_counts[i] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = s_w[lane];
+            uint32_t vi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+                if ((int)lane >= o) vi += t;
+            }
+            s_w[lane] = vi - v;
+            if (lane == 31) s_total = vi;
+        }
+        __syncthreads();
+        if (i < nparts) a.part_bases[i] = carry + s_w[warp] + incl - c;
+        carry += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.counters->num_pairs = carry;
+        a.counters->pair_overflow = (carry > a.uniforms->pair_capacity) ? 1u : 0u;
+    }
+}
+
+// ---- (3) EXPAND ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BIN_THREADS, 4)
+bin_expand_kernel(BinningArgs a)
+{
+    __shared__ uint32_t s_owner[BIN_CAP];             // marker = owner index + 1 at the owner's first position
+    __shared__ uint4 s_info[BIN_PART];                // per splat: {first pair (block-local), x0 | y0<<16, slot, width}
+    __shared__ uint32_t s_magic[BIN_PART];            // ceil(2^32 / width)
+    __shared__ uint32_t s_hist[BIN_NDIG][256];
     __shared__ uint32_t s_scan[BIN_WARPS];
-    __shared__ uint32_t s_part, s_base;
+    __shared__ uint32_t s_wcarry[BIN_WARPS];
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + BIN_THREADS - 1u) / BIN_THREADS;
+    const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
     const uint32_t tiles_x = a.uniforms->tiles_x;
     const uint32_t cap = a.uniforms->pair_capacity;
     const uint32_t ntiles = tiles_x * a.uniforms->tiles_y;
     const int ndig = (ntiles > 65536u) ? 3 : ((ntiles > 256u) ? 2 : 1);
 
-    for (unsigned i = tid; i < 4u * 256u; i += BIN_THREADS) s_hist[i] = 0u;
+    for (unsigned i = tid; i < (unsigned)(BIN_NDIG * 256); i += BIN_THREADS) (&s_hist[0][0])[i] = 0u;
     __syncthreads();
 
-    for (;;) {
-        if (tid == 0) s_part = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t part = s_part;
-        if (part >= nparts) break;
-
-        const uint32_t i = part * BIN_THREADS + tid;
-        uint32_t cnt = 0, slot = 0, xy = 0, w = 0;
-        if (i < V) {
-            slot = a.sorted_slots[i];
-            const uint2 r = a.rects[slot];
-            xy = r.x;
-            w = r.y & 0xffffu;
-            cnt = w * (r.y >> 16);
-        }
-        // block inclusive scan of cnt
-        uint32_t incl = cnt;
+    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
+        SplatRects r;
+        load_rects(a, part * BIN_PART + tid * BIN_SPT, V, r);
+        const uint32_t base = __ldg(a.part_bases + part);
+        const uint32_t mine = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
+        // block scan of the per-thread totals
+        uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -72,100 +175,100 @@ binning_kernel(BinningArgs a)
             if (k < (int)warp) woff += c;
             total += c;
         }
-        incl += woff;
-        s_incl[tid] = incl; s_xy[tid] = xy; s_w[tid] = w; s_slot[tid] = slot;
-
-        if (warp == 0) {
-            // partition totals can exceed 30 bits only if P does; P is capped far below
-            const uint32_t tot30 = total & LB_VALUE_MASK;
-            if (lane == 0 && part > 0u) st_relaxed(a.scan_status + part, LB_AGGREGATE | tot30);
-            uint32_t excl = (part > 0u) ? lookback_warp(a.scan_status, part, &a.counters->error_flags) : 0u;
-            if (lane == 0) {
-                st_relaxed(a.scan_status + part, LB_PREFIX | ((excl + tot30) & LB_VALUE_MASK));
-                s_base = excl;
-                if (part == nparts - 1u) {
-                    const uint32_t P = excl + total;
-                    a.counters->num_pairs = P;
-                    a.counters->pair_overflow = (P > cap) ? 1u : 0u;
-                }
-            }
+        uint32_t excl[BIN_SPT];
+        excl[0] = incl + woff - mine;
+#pragma unroll
+        for (int j = 1; j < BIN_SPT; j++) excl[j] = excl[j - 1] + r.cnt[j - 1];
+#pragma unroll
+        for (int j = 0; j < BIN_SPT; j++) {
+            s_info[tid * BIN_SPT + j] = make_uint4(excl[j], r.xy[j], r.slot[j], r.w[j]);
+            s_magic[tid * BIN_SPT + j] = (r.w[j] > 1u) ? (0xffffffffu / r.w[j] + 1u) : 0u;
         }
-        __syncthreads();
-        const uint32_t base = s_base;
 
-        // ---- load-balanced expansion: pair q of the partition belongs to the splat `owner`
-        //      with s_incl[owner-1] <= q < s_incl[owner]
-        const uint32_t total_r = (total + 31u) & ~31u;       // keep warps converged for match_any
-        for (uint32_t q = tid; q < total_r; q += BIN_THREADS) {
-            const bool ok = q < total;
-            uint32_t tile = 0;
-            if (ok) {
-                int lo = 0, hi = BIN_THREADS - 1;            // first index with s_incl > q
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_incl[mid] > q) hi = mid; else lo = mid + 1;
-                }
-                const uint32_t ow = s_w[lo];
-                const uint32_t start = (lo > 0) ? s_incl[lo - 1] : 0u;   // first pair of the owner's run
-                const uint32_t t = q - start;
-                const uint32_t ty = t / ow, tx = t - ty * ow;
-                const uint32_t oxy = s_xy[lo];
-                tile = ((oxy >> 16) + ty) * tiles_x + (oxy & 0xffffu) + tx;
-                const uint64_t g = (uint64_t)base + q;
-                if (g < cap) {
-                    a.pair_tiles[g] = tile;
-                    a.pair_slots[g] = s_slot[lo];
+        for (uint32_t c0 = 0; c0 < total; c0 += BIN_CAP) {
+            const uint32_t m = (total - c0 < (uint32_t)BIN_CAP) ? total - c0 : (uint32_t)BIN_CAP;
+            const uint32_t rounds = (m + BIN_THREADS - 1u) / BIN_THREADS;       // 32-position rounds per warp
+            const uint32_t span = rounds * 32u;                                 // consecutive positions owned by a warp
+            // 1. clear, 2. markers
+            for (uint32_t q = tid; q < m; q += BIN_THREADS) s_owner[q] = 0u;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < BIN_SPT; j++) {
+                if (r.cnt[j] > 0u) {
+                    if (excl[j] >= c0 && excl[j] < c0 + m) s_owner[excl[j] - c0] = tid * BIN_SPT + j + 1u;
+                    else if (excl[j] < c0 && excl[j] + r.cnt[j] > c0) s_owner[0] = tid * BIN_SPT + j + 1u;   // continues from the previous chunk
                 }
             }
-            const bool counted = ok && ((uint64_t)base + q < cap);
-            for (int d = 0; d < ndig; d++) {
-                const uint32_t dig = (tile >> (8 * d)) & 255u;
-                const unsigned peers = __match_any_sync(0xffffffffu, counted ? dig : 0xffffffffu);
-                if (counted && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[d * 256 + dig], (uint32_t)__popc(peers));
+            __syncthreads();
+            // 3. prefix-max of the markers over this warp's span
+            uint32_t own[BIN_ROUNDS];
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < BIN_ROUNDS; k++) {
+                own[k] = 0u;
+                if ((uint32_t)k < rounds) {
+                    const uint32_t q = warp * span + (uint32_t)k * 32u + lane;
+                    uint32_t v = (q < m) ? s_owner[q] : 0u;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+                        if ((int)lane >= o) v = v > t ? v : t;
+                    }
+                    v = v > carry ? v : carry;
+                    carry = __shfl_sync(0xffffffffu, v, 31);
+                    own[k] = v;
+                }
             }
+            if (lane == 0) s_wcarry[warp] = carry;
+            __syncthreads();
+            uint32_t prev = 0;
+#pragma unroll
+            for (int k = 0; k < BIN_WARPS; k++) if (k < (int)warp) { const uint32_t c = s_wcarry[k]; prev = prev > c ? prev : c; }
+            // 4. emit: position -> (tile, slot), coalesced, plus the tile-id digit histogram
+#pragma unroll
+            for (int k = 0; k < BIN_ROUNDS; k++) {
+                if ((uint32_t)k < rounds) {
+                    const uint32_t q = warp * span + (uint32_t)k * 32u + lane;
+                    const uint64_t g = (uint64_t)base + c0 + q;
+                    if (q < m && g < cap) {
+                        const uint32_t o = (own[k] > prev ? own[k] : prev) - 1u;
+                        const uint4 inf = s_info[o];
+                        const uint32_t t = c0 + q - inf.x;
+                        const uint32_t ty = (inf.w > 1u) ? __umulhi(t, s_magic[o]) : t;
+                        const uint32_t tx = t - ty * inf.w;
+                        const uint32_t tile = ((inf.y >> 16) + ty) * tiles_x + (inf.y & 0xffffu) + tx;
+                        a.pair_tiles[g] = tile;
+                        a.pair_slots[g] = inf.z;
+                        for (int d = 0; d < ndig; d++) atomicAdd(&s_hist[d][(tile >> (8 * d)) & 255u], 1u);
+                    }
+                }
+            }
+            __syncthreads();
         }
         __syncthreads();
     }
 
-    for (unsigned i = tid; i < 4u * 256u; i += BIN_THREADS) {
-        const uint32_t c = s_hist[i];
+    for (unsigned i = tid; i < (unsigned)(ndig * 256); i += BIN_THREADS) {
+        const uint32_t c = s_hist[i >> 8][i & 255u];
         if (c) atomicAdd(a.hist + i, c);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(const uint32_t *__restrict__ pair_tiles, const FrameCounters *counters, uint32_t pair_cap,
-                   uint2 *ranges)
-{
-    uint32_t P = counters->num_pairs;
-    if (P > pair_cap) P = pair_cap;
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < P; i += gridDim.x * 256u) {
-        const uint32_t t = pair_tiles[i];
-        if (i == 0u || pair_tiles[i - 1u] != t) ranges[t].x = i;
-        if (i == P - 1u || pair_tiles[i + 1u] != t) ranges[t].y = i + 1u;
     }
 }
 
 }  // namespace
 
-cudaError_t launch_binning(const BinningArgs &a, int grid, cudaStream_t stream)
+cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand, cudaStream_t stream)
 {
-    binning_kernel<<<grid, BIN_THREADS, 0, stream>>>(a);
+    bin_count_kernel<<<grid_count, BIN_THREADS, 0, stream>>>(a);
+    bin_scan_kernel<<<1, 1024, 0, stream>>>(a);
+    bin_expand_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 int binning_blocks_per_sm()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, binning_kernel, BIN_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bin_expand_kernel, BIN_THREADS, 0);
     return nb > 0 ? nb : 1;
-}
-
-cudaError_t launch_tile_ranges(const uint32_t *pair_tiles, const FrameCounters *counters, uint32_t pair_cap,
-                               uint2 *ranges, int grid, cudaStream_t stream)
-{
-    tile_ranges_kernel<<<grid, 256, 0, stream>>>(pair_tiles, counters, pair_cap, ranges);
-    return cudaGetLastError();
 }
 
 }  // namespace ws

@@ -177,6 +177,7 @@ struct ws_pointcloud {
     uint32_t n, sh_deg;
     bool compressed;
     uint8_t *d_gaussians = nullptr, *d_sh = nullptr, *d_covars = nullptr;
+    float *d_xyz = nullptr;        // position plane (derived from the records at upload) for the count kernel
     Quant4 quant;
     ws_aabb aabb;
     float center[3];
@@ -190,7 +191,7 @@ extern "C" void ws_pointcloud_destroy(ws_pointcloud *pc)
 {
     if (!pc) return;
     cudaSetDevice(pc->ctx->device);
-    cudaFree(pc->d_gaussians); cudaFree(pc->d_sh); cudaFree(pc->d_covars);
+    cudaFree(pc->d_gaussians); cudaFree(pc->d_sh); cudaFree(pc->d_covars); cudaFree(pc->d_xyz);
     delete pc;
 }
 
@@ -226,8 +227,13 @@ extern "C" ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_d
     PC_CU(cudaMalloc(&pc->d_gaussians, gbytes));
     PC_CU(cudaMemset(pc->d_gaussians, 0, gbytes));
     if (n) PC_CU(cudaMemcpy(pc->d_gaussians, d->gaussians, (size_t)n * rec, cudaMemcpyHostToDevice));
-    const size_t shb = d->sh_bytes ? (size_t)d->sh_bytes : 32u;
+    PC_CU(cudaMalloc(&pc->d_xyz, (size_t)(n ? n : 1) * 12u));
+    if (n) PC_CU(cudaMemcpy2D(pc->d_xyz, 12, pc->d_gaussians, rec, 12, n, cudaMemcpyDeviceToDevice));   // xyz is the first 12 B of a record
+    // raw SH is padded to whole 256-record partitions as well (stage 1 bulk-copies 24 KB blocks)
+    size_t shb = d->sh_bytes ? (size_t)d->sh_bytes : 32u;
+    if (!d->compressed && shb < (padded ? padded : 256u) * 96u) shb = (padded ? padded : 256u) * 96u;
     PC_CU(cudaMalloc(&pc->d_sh, shb + 32u));
+    PC_CU(cudaMemset(pc->d_sh, 0, shb + 32u));
     if (d->sh_bytes) PC_CU(cudaMemcpy(pc->d_sh, d->sh_coefs, (size_t)d->sh_bytes, cudaMemcpyHostToDevice));
     if (d->compressed) {
         const size_t cb = (size_t)d->num_covars * 12u;
@@ -272,7 +278,7 @@ extern "C" int32_t ws_pointcloud_dilation_kernel_size(const ws_pointcloud *pc, f
 }
 
 // ------------------------------------------------------------------------------------
-enum { EV_START = 0, EV_PRE, EV_DSORT, EV_BIN, EV_TSORT, EV_RANGES, EV_BLEND0, EV_BLEND1, EV_COUNT };
+enum { EV_START = 0, EV_PRE, EV_DSORT, EV_BIN, EV_TSORT, EV_BLEND0, EV_BLEND1, EV_COUNT };
 enum { TK_PRE = 0, TK_BIN = 1, TK_DSORT = 2, TK_TSORT = 6 };
 
 struct ws_renderer {
@@ -293,8 +299,8 @@ struct ws_renderer {
     uint8_t *d_scratch = nullptr; size_t scratch_bytes = 0;
     FrameCounters *d_counters = nullptr;
     uint32_t *d_hist_depth = nullptr, *d_hist_tile = nullptr;
-    uint32_t *d_scan_pre = nullptr, *d_scan_bin = nullptr;
-    uint32_t *d_status_depth = nullptr, *d_status_tile = nullptr;
+    uint32_t *d_scan_pre = nullptr, *d_scan_bin = nullptr, *d_part_bases = nullptr, *d_bin_bases = nullptr;
+    uint32_t *d_status_depth = nullptr, *d_status_tile = nullptr, *d_gstatus_depth = nullptr, *d_gstatus_tile = nullptr;
     uint32_t *d_splats = nullptr;
     uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
     uint2 *d_rects = nullptr;
@@ -408,8 +414,13 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         const size_t o_ht = off; off = align_up(off + 4 * 256 * 4, 256);
         const size_t o_sp = off; off = align_up(off + parts256 * 4, 256);
         const size_t o_sb = off; off = align_up(off + parts256 * 4, 256);
+        const size_t o_pb = off; off = align_up(off + parts256 * 4, 256);
+        const size_t o_bb = off; off = align_up(off + parts256 * 4, 256);
         const size_t o_sd = off; off = align_up(off + 4 * sparts_n * 256 * 4, 256);
         const size_t o_st = off; off = align_up(off + 3 * sparts_p * 256 * 4, 256);
+        const size_t gparts_n = (sparts_n + SORT_LB_GROUP - 1) / SORT_LB_GROUP, gparts_p = (sparts_p + SORT_LB_GROUP - 1) / SORT_LB_GROUP;
+        const size_t o_gd = off; off = align_up(off + 4 * gparts_n * 256 * 4, 256);
+        const size_t o_gt = off; off = align_up(off + 3 * gparts_p * 256 * 4, 256);
         CU(cudaMalloc(&r->d_scratch, off));
         r->scratch_bytes = off;
         r->d_counters = reinterpret_cast<FrameCounters *>(r->d_scratch + o_counters);
@@ -417,8 +428,12 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         r->d_hist_tile = reinterpret_cast<uint32_t *>(r->d_scratch + o_ht);
         r->d_scan_pre = reinterpret_cast<uint32_t *>(r->d_scratch + o_sp);
         r->d_scan_bin = reinterpret_cast<uint32_t *>(r->d_scratch + o_sb);
+        r->d_part_bases = reinterpret_cast<uint32_t *>(r->d_scratch + o_pb);
+        r->d_bin_bases = reinterpret_cast<uint32_t *>(r->d_scratch + o_bb);
         r->d_status_depth = reinterpret_cast<uint32_t *>(r->d_scratch + o_sd);
         r->d_status_tile = reinterpret_cast<uint32_t *>(r->d_scratch + o_st);
+        r->d_gstatus_depth = reinterpret_cast<uint32_t *>(r->d_scratch + o_gd);
+        r->d_gstatus_tile = reinterpret_cast<uint32_t *>(r->d_scratch + o_gt);
         CU(cudaMalloc(&r->d_splats, nn * 20));
         for (int i = 0; i < 2; i++) {
             CU(cudaMalloc(&r->d_keys[i], nn * 4));
@@ -485,17 +500,17 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     // pageable source: the runtime stages the 0.5 KB before returning, so h_uniforms may be reused
     CU(cudaMemcpyAsync(r->d_uniforms, &U, sizeof U, cudaMemcpyHostToDevice, stream));
     CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
-    CU(cudaMemsetAsync(r->d_ranges, 0, (size_t)tiles * 8, stream));
+    CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)tiles * 8, stream));    // {begin, ~end} identities for atomicMin
 
     if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
     {   // ---- stage 1
         PreprocessArgs a;
-        a.gaussians = pc->d_gaussians; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
+        a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
         a.uniforms = r->d_uniforms;
         a.splats = r->d_splats; a.depth_keys = r->d_keys[0]; a.slot_vals = r->d_vals[0]; a.rects = r->d_rects;
-        a.scan_status = r->d_scan_pre; a.ticket = &r->d_counters->ticket[TK_PRE];
+        a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
         a.hist = r->d_hist_depth; a.counters = r->d_counters;
-        CU(launch_preprocess(a, r->compressed, r->grid_pre, stream));
+        CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
     {   // ---- stage 2a: depth passes on the V visible splats
@@ -507,6 +522,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
             a.keys_out = r->d_keys[src ^ 1]; a.vals_out = r->d_vals[src ^ 1];
             a.n_ptr = &r->d_counters->num_visible; a.n_cap = r->n_cap;
             a.status = r->d_status_depth + (size_t)p * sparts_n * 256;
+            a.gstatus = r->d_gstatus_depth + (size_t)p * ((sparts_n + SORT_LB_GROUP - 1) / SORT_LB_GROUP) * 256;
+            a.ranges = nullptr;
             a.ticket = &r->d_counters->ticket[TK_DSORT + p];
             a.hist = r->d_hist_depth + p * 256;
             a.shift = 8u * (uint32_t)p;
@@ -521,8 +538,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
         BinningArgs a;
         a.sorted_slots = r->d_vals[r->depth_out]; a.rects = r->d_rects; a.uniforms = r->d_uniforms;
         a.counters = r->d_counters; a.pair_tiles = r->d_ptiles[0]; a.pair_slots = r->d_pslots[0];
-        a.scan_status = r->d_scan_bin; a.ticket = &r->d_counters->ticket[TK_BIN]; a.hist = r->d_hist_tile;
-        CU(launch_binning(a, r->grid_bin, stream));
+        a.part_counts = r->d_scan_bin; a.part_bases = r->d_bin_bases; a.hist = r->d_hist_tile;
+        CU(launch_binning(a, r->ctx->sm_count * 8, r->grid_bin, stream));
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_BIN], stream));
     {   // ---- stage 2c: tile-id passes on the P pairs
@@ -534,6 +551,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
             a.keys_out = r->d_ptiles[src ^ 1]; a.vals_out = r->d_pslots[src ^ 1];
             a.n_ptr = &r->d_counters->num_pairs; a.n_cap = r->pair_cap;
             a.status = r->d_status_tile + (size_t)p * sparts_p * 256;
+            a.gstatus = r->d_gstatus_tile + (size_t)p * ((sparts_p + SORT_LB_GROUP - 1) / SORT_LB_GROUP) * 256;
+            a.ranges = (p == r->tile_passes - 1) ? r->d_ranges : nullptr;     // the last pass also emits the tile ranges
             a.ticket = &r->d_counters->ticket[TK_TSORT + p];
             a.hist = r->d_hist_tile + p * 256;
             a.shift = 8u * (uint32_t)p;
@@ -544,8 +563,6 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
         r->tile_out = src;
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_TSORT], stream));
-    CU(launch_tile_ranges(r->d_ptiles[r->tile_out], r->d_counters, r->pair_cap, r->d_ranges, r->ctx->sm_count * 8, stream));
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_RANGES], stream));
 
     r->prepared = true;
     r->last_stream = stream;
@@ -639,8 +656,8 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
         s->ms_depth_sort = el(EV_PRE, EV_DSORT);
         s->ms_binning = el(EV_DSORT, EV_BIN);
         s->ms_tile_sort = el(EV_BIN, EV_TSORT);
-        s->ms_ranges = el(EV_TSORT, EV_RANGES);
-        s->ms_sort = el(EV_PRE, EV_RANGES);
+        s->ms_ranges = 0.f;                                   // fused into the last tile-sort pass
+        s->ms_sort = el(EV_PRE, EV_TSORT);
         if (r->rendered) s->ms_blend = el(EV_BLEND0, EV_BLEND1);
         cudaGetLastError();
     }
@@ -650,8 +667,8 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
     const uint64_t rec = r->compressed ? 24 : 28;
     const uint64_t ncoef = (uint64_t)(U.rs.max_sh_deg + 1) * (U.rs.max_sh_deg + 1);
     const uint64_t shb = r->compressed ? (12 + 3 * ncoef) : (U.rs.max_sh_deg >= 3 ? 96 : (U.rs.max_sh_deg == 2 ? 64 : 32));
-    s->bytes_preprocess = N * rec + V * shb + V * (20 + 4 + 4 + 8);
-    s->bytes_sort = (uint64_t)r->depth_passes * V * 16 + V * 12 + P * 8 + (uint64_t)r->tile_passes * P * 16 + P * 4 + T * 8;
+    s->bytes_preprocess = N * 12 + N * rec + V * shb + V * (20 + 4 + 4 + 8);   // count (xyz plane) + main
+    s->bytes_sort = (uint64_t)r->depth_passes * V * 16 + V * 12 + P * 8 + (uint64_t)r->tile_passes * P * 16 + T * 8;
     s->bytes_blend = P * 24 + T * 8 + (uint64_t)U.width * U.height * bytes_per_pixel(r->format);
     if (c.error_flags) return fail(WS_ERR_CUDA, "internal: decoupled look-back watchdog fired");
     if (c.pair_overflow) return fail(WS_ERR_PAIR_OVERFLOW, "pair capacity exceeded; raise it with ws_renderer_set_pair_capacity");
@@ -697,6 +714,13 @@ extern "C" ws_status ws_renderer_read_buffer(ws_renderer *r, ws_buffer_id which,
         return WS_OK;
     }
     if (bytes) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    if (which == WS_BUF_TILE_RANGES) {      // device form is {begin, ~end} with 0xffffffff identities
+        uint32_t *o = static_cast<uint32_t *>(dst);
+        for (size_t t = 0; t < T; t++) {
+            const uint32_t b = o[2 * t], e = ~o[2 * t + 1];
+            if (e <= b) { o[2 * t] = 0; o[2 * t + 1] = 0; } else { o[2 * t + 1] = e; }
+        }
+    }
     return WS_OK;
 }
 
@@ -727,7 +751,8 @@ extern "C" ws_status ws_sort_pairs_u32(ws_context *ctx, uint32_t *keys, uint32_t
     const int passes = (int)((key_bits + 7) / 8);
     const size_t sparts = ((size_t)n + SORT_PART - 1) / SORT_PART;
     // scratch: [n u32][tickets 4][hist 4*256][status passes*sparts*256] + ping-pong buffers
-    const size_t scratch_words = 8 + 4 * 256 + (size_t)passes * sparts * 256;
+    const size_t gparts = (sparts + SORT_LB_GROUP - 1) / SORT_LB_GROUP;
+    const size_t scratch_words = 8 + 4 * 256 + (size_t)passes * (sparts + gparts) * 256;
     uint32_t *scratch = nullptr, *k2 = nullptr, *v2 = nullptr;
     CU(cudaMalloc(&scratch, scratch_words * 4));
     cudaError_t e = cudaMalloc(&k2, (size_t)n * 4);
@@ -738,6 +763,7 @@ extern "C" ws_status ws_sort_pairs_u32(ws_context *ctx, uint32_t *keys, uint32_t
         e = cudaMemsetAsync(scratch, 0, scratch_words * 4, stream); if (e != cudaSuccess) break;
         e = cudaMemcpyAsync(scratch, &n, 4, cudaMemcpyHostToDevice, stream); if (e != cudaSuccess) break;
         uint32_t *n_ptr = scratch, *tickets = scratch + 4, *hist = scratch + 8, *status = scratch + 8 + 4 * 256;
+        uint32_t *gstatus = status + (size_t)passes * sparts * 256;
         e = launch_sort_histogram(keys, n_ptr, n, hist, passes, ctx->sm_count * 4, stream); if (e != cudaSuccess) break;
         const int grid = ctx->sm_count * sort_pass_blocks_per_sm();
         uint32_t *kb[2] = {keys, k2}, *vb[2] = {vals, v2};
@@ -747,6 +773,7 @@ extern "C" ws_status ws_sort_pairs_u32(ws_context *ctx, uint32_t *keys, uint32_t
             a.keys_in = kb[src]; a.vals_in = vb[src]; a.keys_out = kb[src ^ 1]; a.vals_out = vb[src ^ 1];
             a.n_ptr = n_ptr; a.n_cap = n; a.status = status + (size_t)p * sparts * 256; a.ticket = tickets + p;
             a.hist = hist + p * 256; a.shift = 8u * (uint32_t)p; a.err = nullptr;
+            a.gstatus = gstatus + (size_t)p * gparts * 256; a.ranges = nullptr;
             e = launch_sort_pass(a, grid, stream);
             src ^= 1;
         }

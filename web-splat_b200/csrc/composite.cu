@@ -48,7 +48,9 @@ composite_kernel(CompositeArgs a)
     const uint32_t W = a.uniforms->width, H = a.uniforms->height;
     const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
     const uint32_t tile = tile_y * gridDim.x + tile_x;
-    const uint2 range = a.ranges[tile];
+    uint2 range = a.ranges[tile];
+    range.y = ~range.y;                                  // stored complemented (atomicMin in the sort's last pass)
+    if (range.y <= range.x) range.x = range.y = 0u;      // untouched tile
     const float fw = (float)W, fh = (float)H;
     const float hw = 0.5f * fw, hh = 0.5f * fh;
     const float ox = hw - (float)(tile_x * TILE), oy = hh - (float)(tile_y * TILE);   // exact

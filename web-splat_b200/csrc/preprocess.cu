@@ -6,16 +6,22 @@
 // rectangle and the digit histograms of the depth keys for the onesweep that follows.
 //
 // B200 design notes
-//  * persistent CTAs take 256-Gaussian partitions from an atomic ticket; the 28-B (24-B)
-//    AoS records of a partition are staged with ONE cp.async.bulk (TMA engine, UBLKCP)
-//    into shared memory and read from there at a conflict-free 7-word (6-word: 2-way)
-//    stride, so HBM sees only full, coalesced 7168-B (6144-B) bursts;
-//  * SH (96 B per survivor) is fetched with three 256-bit loads per lane: one full
-//    32-B sector per request, no sector is requested twice;
-//  * compaction is deterministic: ballot + block scan + single-pass decoupled look-back
-//    over the ticket-ordered partitions (the reference uses one contended global atomic,
-//    preprocess.wgsl:262, which also makes its slot order nondeterministic);
-//  * outputs are staged through shared memory and leave as coalesced streams;
+//  * three launches: (1) COUNT reads only a 12-B xyz plane, culls, writes the number of
+//    survivors of every 256-Gaussian partition and the digit histograms of their depth keys;
+//    (2) a one-CTA SCAN turns the counts into slot offsets; (3) MAIN does the projection.
+//    Compaction is therefore deterministic (slot order = Gaussian index order; the reference
+//    uses one contended global atomic, preprocess.wgsl:262, whose order is not), and MAIN has
+//    no inter-CTA dependency at all -- a single-pass chained scan was tried first (r01a/r01b in
+//    profiles/): its look-back serialised the prefetch pipeline.  The price is re-reading xyz:
+//    +12 B on top of 124 B per Gaussian;
+//  * MAIN is software-pipelined: partitions are assigned round-robin, the 28-B (24-B) AoS
+//    records of partition k+2 and -- when at least half of it survives -- its 24-KB SH block
+//    are fetched by cp.async.bulk (TMA engine, UBLKCP) into shared-memory rings while
+//    partition k is being computed; ~100 KB per SM are in flight, HBM sees only full bursts;
+//    sparse partitions fetch SH with three 256-bit loads per surviving lane instead
+//    (one full 32-B sector per request);
+//  * records are read from shared memory at a conflict-free 7-word (6-word: 2-way) stride;
+//    outputs are staged through shared memory and leave as coalesced streams;
 //  * this file is compiled with -fmad=false: every f32 operation rounds once, in the
 //    order written, which makes stage 1 bit-identical to the CPU oracle (raw layout).
 #include "ws_device.cuh"
@@ -128,6 +134,19 @@ struct Stage1 {
     uint32_t rect_wh;       // w  | h  << 16  (w == 0: touches no tile)
 };
 
+// sort key: preprocess.wgsl:270-273 (f32 bits of zfar - clip.z) / compressed :321-325 (24-bit integer)
+template <bool COMPRESSED>
+__device__ __forceinline__ uint32_t depth_key(const FrameUniforms &U, float p2)
+{
+    const float znear = -U.cam.proj[3 * 4 + 2] / U.cam.proj[2 * 4 + 2];
+    const float zfar = -U.cam.proj[3 * 4 + 2] / (U.cam.proj[2 * 4 + 2] - 1.f);
+    if (!COMPRESSED) return __float_as_uint(zfar - p2);
+    const float kf = 16777215.f - (p2 - znear) / (zfar - znear) * 16777215.f;
+    if (!(kf > 0.f)) return 0u;
+    if (kf >= 4294967296.f) return 0xffffffffu;
+    return (uint32_t)kf;
+}
+
 // Everything after the cull: preprocess.wgsl:194-279 / compressed :235-330.
 template <bool COMPRESSED, class SH>
 __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, float y, float z,
@@ -223,16 +242,7 @@ __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, fl
     o.splat[3] = pack2h(col.x, col.y);
     o.splat[4] = pack2h(col.z, opacity);
 
-    const float znear = -U.cam.proj[3 * 4 + 2] / U.cam.proj[2 * 4 + 2];
-    const float zfar = -U.cam.proj[3 * 4 + 2] / (U.cam.proj[2 * 4 + 2] - 1.f);
-    if (!COMPRESSED) {
-        o.key = __float_as_uint(zfar - p2);
-    } else {
-        float kf = 16777215.f - (p2 - znear) / (zfar - znear) * 16777215.f;
-        uint32_t k;
-        if (!(kf > 0.f)) k = 0u; else if (kf >= 4294967296.f) k = 0xffffffffu; else k = (uint32_t)kf;
-        o.key = k;
-    }
+    o.key = depth_key<COMPRESSED>(U, p2);
 
     // ---- tile rectangle of the STORED (f16-rounded) splat; must equal oracle wso_tile_rects ----
     {
@@ -260,107 +270,241 @@ __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, fl
     }
 }
 
+// Cull + clip-space projection of one record: preprocess.wgsl:177-192 / compressed :223-233.
 template <bool COMPRESSED>
-__global__ void __launch_bounds__(PP_THREADS, 2)
-preprocess_kernel(PreprocessArgs a)
+__device__ __forceinline__ bool cull_project(const FrameUniforms &U, float x, float y, float z, float cs[4], float pp[4])
 {
-    constexpr uint32_t REC = COMPRESSED ? 24u : 28u;
-    constexpr uint32_t REC_WORDS = REC / 4u;
-    __shared__ __align__(128) uint32_t s_rec[PP_THREADS * REC_WORDS];
-    __shared__ __align__(16) uint32_t s_splat[PP_THREADS * 5];
-    __shared__ uint32_t s_key[PP_THREADS];
-    __shared__ uint2 s_rect[PP_THREADS];
-    __shared__ uint32_t s_hist[4 * 256];
+    // clip box (:177) -- any(xyz < min) || any(xyz > max)
+    if (x < U.rs.clip_min[0] || y < U.rs.clip_min[1] || z < U.rs.clip_min[2] ||
+        x > U.rs.clip_max[0] || y > U.rs.clip_max[1] || z > U.rs.clip_max[2]) return false;
+    const float *view = U.cam.view, *proj = U.cam.proj;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        float acc = view[0 * 4 + r] * x;
+        acc = acc + view[1 * 4 + r] * y;
+        acc = acc + view[2 * 4 + r] * z;
+        acc = acc + view[3 * 4 + r] * 1.f;
+        cs[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        float acc = proj[0 * 4 + r] * cs[0];
+        acc = acc + proj[1 * 4 + r] * cs[1];
+        acc = acc + proj[2 * 4 + r] * cs[2];
+        acc = acc + proj[3 * 4 + r] * cs[3];
+        pp[r] = acc;
+    }
+    const float bounds = 1.2f * pp[3];
+    const float zz = pp[2] / pp[3];
+    if (!COMPRESSED) {
+        if (zz <= 0.f || zz >= 1.f || pp[0] < -bounds || pp[0] > bounds || pp[1] < -bounds || pp[1] > bounds) return false;
+    } else {
+        if (zz < 0.f || zz > 1.f || pp[0] < -bounds || pp[0] > bounds || pp[1] < -bounds || pp[1] > bounds) return false;
+    }
+    return true;
+}
+
+// ---- (1) COUNT: survivors per partition + depth-key digit histograms -----------------------
+template <bool COMPRESSED>
+__global__ void __launch_bounds__(PP_THREADS)
+count_kernel(PreprocessArgs a)
+{
     __shared__ FrameUniforms s_u;
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_warp_cnt[PP_WARPS];
-    __shared__ uint32_t s_part, s_base;
-
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-
-    {   // uniforms -> smem
+    __shared__ uint32_t s_hist[4 * 256];
+    const unsigned tid = threadIdx.x;
+    {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.uniforms);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_u);
         for (unsigned i = tid; i < sizeof(FrameUniforms) / 4u; i += PP_THREADS) dst[i] = src[i];
     }
     for (unsigned i = tid; i < 4u * 256u; i += PP_THREADS) s_hist[i] = 0u;
-    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     __syncthreads();
     const FrameUniforms &U = s_u;
     const uint32_t n = U.num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
-    uint32_t parity = 0;
-
-    for (;;) {
-        if (tid == 0) s_part = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t part = s_part;
-        if (part >= nparts) break;
-
-        // ---- stage the partition's AoS records: one bulk copy (buffer is padded to a full partition)
-        if (tid == 0) {
-            fence_proxy_async();   // order prior generic-proxy reads of s_rec before the async-proxy write
-            mbar_arrive_expect_tx(&s_bar, PP_THREADS * REC);
-            bulk_g2s(s_rec, a.gaussians + (size_t)part * (PP_THREADS * REC), PP_THREADS * REC, &s_bar);
+    constexpr int NDIG = COMPRESSED ? 3 : 4;
+    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
+        const uint32_t idx = part * PP_THREADS + tid;
+        bool keep = false;
+        uint32_t key = 0;
+        if (idx < n) {
+            const float *p = a.xyz + (size_t)idx * 3u;
+            float cs[4], pp[4];
+            keep = cull_project<COMPRESSED>(U, __ldg(p), __ldg(p + 1), __ldg(p + 2), cs, pp);
+            key = depth_key<COMPRESSED>(U, pp[2]);
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1u;
+        const uint32_t cnt = (uint32_t)__syncthreads_count(keep ? 1 : 0);
+        if (tid == 0) a.part_counts[part] = cnt;
+        // shared atomics without return sustain ~120 G warp-ops/s on B200 whatever the spread
+        // (profiles/microbench/rank_primitives.cu); MATCH-aggregating them was 25x slower
+        if (keep) {
+#pragma unroll
+            for (int d = 0; d < NDIG; d++) atomicAdd(&s_hist[d * 256 + ((key >> (8 * d)) & 255u)], 1u);
+        }
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < (unsigned)NDIG * 256u; i += PP_THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(a.hist + i, c);
+    }
+}
 
+// ---- (2) SCAN: exclusive scan of the partition counts (one CTA) ------------------------------
+__global__ void __launch_bounds__(1024)
+scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, const FrameUniforms *uniforms,
+            FrameCounters *counters)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_total;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n = uniforms->num_points;
+    const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < nparts; b += 1024u) {
+        const uint32_t i = b + tid;
+        const uint32_t c = (i < nparts) ? counts[i] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = s_w[lane];
+            uint32_t vi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+                if ((int)lane >= o) vi += t;
+            }
+            s_w[lane] = vi - v;                       // exclusive offset of each warp
+            if (lane == 31) s_total = vi;             // chunk total
+        }
+        __syncthreads();
+        if (i < nparts) bases[i] = carry + s_w[warp] + incl - c;
+        carry += s_total;
+        __syncthreads();
+    }
+    if (tid == 0) counters->num_visible = carry;
+}
+
+// ---- (3) MAIN ---------------------------------------------------------------------------------
+constexpr int PP_STAGES = 3;                         // ring depth: records and SH of k+1, k+2 in flight
+constexpr uint32_t PP_SH_BYTES = PP_THREADS * 96u;   // one partition's SH block
+constexpr uint32_t PP_SH_BULK_MIN = 128;             // bulk-stage the SH block when >= half the partition survives
+
+template <bool COMPRESSED>
+struct PPSmem {
+    static constexpr uint32_t REC = COMPRESSED ? 24u : 28u;
+    static constexpr uint32_t REC_BYTES = PP_THREADS * REC;
+    static constexpr uint32_t off_rec = 0;
+    static constexpr uint32_t off_sh = off_rec + PP_STAGES * REC_BYTES;                        // 128-B aligned (7168, 6144)
+    static constexpr uint32_t off_splat = off_sh + (COMPRESSED ? 0u : PP_STAGES * PP_SH_BYTES);
+    static constexpr uint32_t off_key = off_splat + PP_THREADS * 20u;
+    static constexpr uint32_t off_rect = off_key + PP_THREADS * 4u;
+    static constexpr uint32_t off_u = off_rect + PP_THREADS * 8u;
+    static constexpr uint32_t off_bar = (off_u + (uint32_t)sizeof(FrameUniforms) + 15u) & ~15u;
+    static constexpr uint32_t off_misc = off_bar + 8u * (2 * PP_STAGES);
+    static constexpr uint32_t bytes = off_misc + 64u;
+};
+
+template <bool COMPRESSED>
+__global__ void __launch_bounds__(PP_THREADS, 2)
+preprocess_kernel(PreprocessArgs a)
+{
+    using L = PPSmem<COMPRESSED>;
+    constexpr uint32_t REC = L::REC, REC_WORDS = REC / 4u;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *s_splat = reinterpret_cast<uint32_t *>(smem + L::off_splat);
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(smem + L::off_key);
+    uint2 *s_rect = reinterpret_cast<uint2 *>(smem + L::off_rect);
+    FrameUniforms &s_u = *reinterpret_cast<FrameUniforms *>(smem + L::off_u);
+    uint64_t *s_rbar = reinterpret_cast<uint64_t *>(smem + L::off_bar);
+    uint64_t *s_sbar = s_rbar + PP_STAGES;
+    uint32_t *s_warp_cnt = reinterpret_cast<uint32_t *>(smem + L::off_misc);      // [8]
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    {   // uniforms -> smem
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.uniforms);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_u);
+        for (unsigned i = tid; i < sizeof(FrameUniforms) / 4u; i += PP_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2 * PP_STAGES; i++) mbar_init(&s_rbar[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const FrameUniforms &U = s_u;
+    const uint32_t n = U.num_points;
+    const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
+    const bool sh_bulk_ok = !COMPRESSED && U.rs.max_sh_deg >= 2u;
+
+    // iteration k of this CTA handles partition blockIdx.x + k * gridDim.x
+    auto part_of = [&](uint32_t k) -> uint32_t { return blockIdx.x + k * gridDim.x; };
+    auto uses_bulk_sh = [&](uint32_t part) -> bool { return sh_bulk_ok && __ldg(a.part_counts + part) >= PP_SH_BULK_MIN; };
+    auto issue = [&](uint32_t k) {                    // thread 0 only: fetch everything partition k needs
+        const uint32_t part = part_of(k);
+        if (part >= nparts) return;
+        const uint32_t s = k % PP_STAGES;
+        fence_proxy_async();                          // earlier generic-proxy reads of the slot happen-before the async write
+        mbar_arrive_expect_tx(&s_rbar[s], L::REC_BYTES);
+        bulk_g2s(smem + L::off_rec + s * L::REC_BYTES, a.gaussians + (size_t)part * L::REC_BYTES, L::REC_BYTES, &s_rbar[s]);
+        if (uses_bulk_sh(part)) {
+            mbar_arrive_expect_tx(&s_sbar[s], PP_SH_BYTES);
+            bulk_g2s(smem + L::off_sh + s * PP_SH_BYTES, a.sh_coefs + (size_t)part * PP_SH_BYTES, PP_SH_BYTES, &s_sbar[s]);
+        }
+    };
+
+    if (tid == 0) { issue(0); issue(1); }
+    uint32_t rpar = 0, spar = 0;                      // per-slot mbarrier phase parities (block-uniform)
+
+    for (uint32_t k = 0;; k++) {
+        const uint32_t part = part_of(k);
+        if (part >= nparts) break;
+        const uint32_t s = k % PP_STAGES;
+        if (tid == 0) issue(k + 2u);                  // slot (k+2)%3 was last read in iteration k-1 (trailing barrier)
+
+        const bool bulk = uses_bulk_sh(part);
+        mbar_wait(&s_rbar[s], (rpar >> s) & 1u); rpar ^= 1u << s;
+        if (bulk) { mbar_wait(&s_sbar[s], (spar >> s) & 1u); spar ^= 1u << s; }
+
+        const uint32_t *rec = reinterpret_cast<const uint32_t *>(smem + L::off_rec + s * L::REC_BYTES) + tid * REC_WORDS;
         const uint32_t idx = part * PP_THREADS + tid;
         bool vis = false;
         Stage1 o;
         o.key = 0u; o.rect_xy = 0u; o.rect_wh = 0u;
         o.splat[0] = o.splat[1] = o.splat[2] = o.splat[3] = o.splat[4] = 0u;
         if (idx < n) {
-            const uint32_t *rec = s_rec + tid * REC_WORDS;
             const float x = __uint_as_float(rec[0]), y = __uint_as_float(rec[1]), z = __uint_as_float(rec[2]);
-            // clip box (:177) -- any(xyz < min) || any(xyz > max)
-            bool keep = !(x < U.rs.clip_min[0] || y < U.rs.clip_min[1] || z < U.rs.clip_min[2] ||
-                          x > U.rs.clip_max[0] || y > U.rs.clip_max[1] || z > U.rs.clip_max[2]);
             float cs[4], pp[4];
-            if (keep) {
-                const float *view = U.cam.view, *proj = U.cam.proj;
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    float acc = view[0 * 4 + r] * x;
-                    acc = acc + view[1 * 4 + r] * y;
-                    acc = acc + view[2 * 4 + r] * z;
-                    acc = acc + view[3 * 4 + r] * 1.f;
-                    cs[r] = acc;
-                }
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    float acc = proj[0 * 4 + r] * cs[0];
-                    acc = acc + proj[1 * 4 + r] * cs[1];
-                    acc = acc + proj[2 * 4 + r] * cs[2];
-                    acc = acc + proj[3 * 4 + r] * cs[3];
-                    pp[r] = acc;
-                }
-                const float bounds = 1.2f * pp[3];
-                const float zz = pp[2] / pp[3];
-                if (!COMPRESSED) {
-                    if (zz <= 0.f || zz >= 1.f || pp[0] < -bounds || pp[0] > bounds || pp[1] < -bounds || pp[1] > bounds) keep = false;
-                } else {
-                    if (zz < 0.f || zz > 1.f || pp[0] < -bounds || pp[0] > bounds || pp[1] < -bounds || pp[1] > bounds) keep = false;
-                }
-            }
-            if (keep) {
+            if (cull_project<COMPRESSED>(U, x, y, z, cs, pp)) {
                 vis = true;
                 if (!COMPRESSED) {
                     const float opacity = half_lo(rec[3]);
                     const float cov6[6] = {half_lo(rec[4]), half_hi(rec[4]), half_lo(rec[5]),
                                            half_hi(rec[5]), half_lo(rec[6]), half_hi(rec[6])};
                     ShRaw sh;
-                    const uint8_t *sp = a.sh_coefs + (size_t)idx * 96u;
                     const uint32_t deg = U.rs.max_sh_deg;
-                    ldg256(sp, sh.w);
-                    if (deg > 1u) ldg256(sp + 32, sh.w + 8); else {
+                    if (bulk) {
+                        const uint4 *sp = reinterpret_cast<const uint4 *>(smem + L::off_sh + s * PP_SH_BYTES + tid * 96u);
 #pragma unroll
-                        for (int i = 8; i < 16; i++) sh.w[i] = 0u;
-                    }
-                    if (deg > 2u) ldg256(sp + 64, sh.w + 16); else {
+                        for (int q = 0; q < 6; q++) {
+                            const uint4 v = sp[q];
+                            sh.w[4 * q] = v.x; sh.w[4 * q + 1] = v.y; sh.w[4 * q + 2] = v.z; sh.w[4 * q + 3] = v.w;
+                        }
+                    } else {
+                        const uint8_t *sp = a.sh_coefs + (size_t)idx * 96u;
+                        ldg256(sp, sh.w);
+                        if (deg > 1u) ldg256(sp + 32, sh.w + 8); else {
 #pragma unroll
-                        for (int i = 16; i < 24; i++) sh.w[i] = 0u;
+                            for (int i = 8; i < 16; i++) sh.w[i] = 0u;
+                        }
+                        if (deg > 2u) ldg256(sp + 64, sh.w + 16); else {
+#pragma unroll
+                            for (int i = 16; i < 24; i++) sh.w[i] = 0u;
+                        }
                     }
                     project_tail<false>(U, x, y, z, cs[0], cs[1], cs[2], pp[0], pp[1], pp[2], pp[3], cov6, opacity, sh, o);
                 } else {
@@ -383,7 +527,7 @@ preprocess_kernel(PreprocessArgs a)
             }
         }
 
-        // ---- deterministic compaction: ballot, block scan, decoupled look-back ----
+        // ---- deterministic compaction: slot = scanned partition base + rank inside the partition
         const unsigned bal = __ballot_sync(0xffffffffu, vis);
         if (lane == 0) s_warp_cnt[warp] = __popc(bal);
         __syncthreads();
@@ -394,34 +538,15 @@ preprocess_kernel(PreprocessArgs a)
             if (w < (int)warp) warp_off += c;
             total += c;
         }
-        if (warp == 0) {
-            if (lane == 0 && part > 0u) st_relaxed(a.scan_status + part, LB_AGGREGATE | total);
-            uint32_t excl = (part > 0u) ? lookback_warp(a.scan_status, part, &a.counters->error_flags) : 0u;
-            if (lane == 0) {
-                st_relaxed(a.scan_status + part, LB_PREFIX | (excl + total));
-                s_base = excl;
-                if (part == nparts - 1u) a.counters->num_visible = excl + total;
-            }
-        }
         const uint32_t local = warp_off + __popc(bal & lanemask_lt());
         if (vis) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) s_splat[local * 5u + k] = o.splat[k];
+            for (int q = 0; q < 5; q++) s_splat[local * 5u + q] = o.splat[q];
             s_key[local] = o.key;
             s_rect[local] = make_uint2(o.rect_xy, o.rect_wh);
         }
-        // depth-key digit histograms for the onesweep (warp-aggregated: the upper digits of
-        // a float key take only a handful of values, plain smem atomics would serialise)
-        {
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const uint32_t dig = (o.key >> (8 * d)) & 255u;
-                const unsigned peers = __match_any_sync(0xffffffffu, vis ? dig : 0xffffffffu);
-                if (vis && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[d * 256 + dig], (uint32_t)__popc(peers));
-            }
-        }
         __syncthreads();
-        const uint32_t base = s_base;
+        const uint32_t base = __ldg(a.part_bases + part);
         // ---- coalesced output streams ----
         for (uint32_t i = tid; i < total * 5u; i += PP_THREADS) a.splats[(size_t)base * 5u + i] = s_splat[i];
         if (tid < total) {
@@ -431,28 +556,42 @@ preprocess_kernel(PreprocessArgs a)
         }
         __syncthreads();
     }
-
-    // flush the CTA's digit histograms
-    for (unsigned i = tid; i < 4u * 256u; i += PP_THREADS) {
-        uint32_t c = s_hist[i];
-        if (c) atomicAdd(a.hist + i, c);
-    }
 }
 
 }  // namespace
 
-cudaError_t launch_preprocess(const PreprocessArgs &a, bool compressed, int grid, cudaStream_t stream)
+template <bool C>
+static cudaError_t pp_prepare()
 {
-    if (compressed) preprocess_kernel<true><<<grid, PP_THREADS, 0, stream>>>(a);
-    else preprocess_kernel<false><<<grid, PP_THREADS, 0, stream>>>(a);
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PPSmem<C>::bytes);
+    if (e == cudaSuccess) done = true;
+    return e;
+}
+
+cudaError_t launch_preprocess(const PreprocessArgs &a, bool compressed, int grid_count, int grid_main, cudaStream_t stream)
+{
+    cudaError_t e = compressed ? pp_prepare<true>() : pp_prepare<false>();
+    if (e != cudaSuccess) return e;
+    if (compressed) count_kernel<true><<<grid_count, PP_THREADS, 0, stream>>>(a);
+    else count_kernel<false><<<grid_count, PP_THREADS, 0, stream>>>(a);
+    scan_kernel<<<1, 1024, 0, stream>>>(a.part_counts, a.part_bases, a.uniforms, a.counters);
+    if (compressed) preprocess_kernel<true><<<grid_main, PP_THREADS, PPSmem<true>::bytes, stream>>>(a);
+    else preprocess_kernel<false><<<grid_main, PP_THREADS, PPSmem<false>::bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
 int preprocess_blocks_per_sm(bool compressed)
 {
     int nb = 0;
-    if (compressed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, preprocess_kernel<true>, PP_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, preprocess_kernel<false>, PP_THREADS, 0);
+    if (compressed) {
+        if (pp_prepare<true>() != cudaSuccess) return 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, preprocess_kernel<true>, PP_THREADS, PPSmem<true>::bytes);
+    } else {
+        if (pp_prepare<false>() != cudaSuccess) return 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, preprocess_kernel<false>, PP_THREADS, PPSmem<false>::bytes);
+    }
     return nb > 0 ? nb : 1;
 }
 

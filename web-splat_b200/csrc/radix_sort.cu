@@ -6,13 +6,24 @@
 //   * persistent CTAs take 4096-pair partitions from an atomic ticket (forward progress
 //     for the decoupled look-back does not depend on the hardware's CTA scheduling order,
 //     which radix_sort.wgsl:365-387 silently relies on);
-//   * ranking uses the warp MATCH instruction (one __match_any_sync per key) instead of
-//     the reference's per-key shared-memory loop emulation (radix_sort.wgsl:283-302);
-//   * 256 threads each run the decoupled look-back of one digit bin, on single 32-bit
-//     status words (2-bit flag | 30-bit count) so relaxed accesses are sufficient;
-//   * keys/values are reordered in shared memory and leave as per-bin contiguous runs.
+//   * ranking: each lane ORs its lane bit into a per-warp, per-digit peer mask in shared memory
+//     (atomicOr without return), reads the mask back and the lowest peer bumps the warp's
+//     private digit counter with a plain read-modify-write.  Measured on B200
+//     (profiles/microbench/rank_primitives.cu): MATCH.ANY on random 8-bit digits sustains only
+//     4.7 G warp-ops/s chip-wide (its cost grows with the number of distinct values), an
+//     8-ballot emulation 11.5 G, shared atomics without return 118-135 G; the reference
+//     emulates match with a per-key shared-memory loop (radix_sort.wgsl:283-302);
+//   * decoupled look-back, one thread per digit bin, on single 32-bit status words
+//     (2-bit flag | 30-bit count: relaxed accesses suffice), TWO levels deep: partitions are
+//     grouped by 16 and the last partition of a group publishes the group's aggregate /
+//     inclusive prefix.  A persistent grid starts W partitions at once, none of which has a
+//     prefix yet; a flat look-back then reads W^2/2 status rows (100 MB of L2 traffic for
+//     W=444), the two-level one 15 + W/16 rows per partition;
+//   * keys/values are reordered in shared memory and leave as per-bin contiguous runs;
+//   * the last tile-id pass also emits the per-tile [begin,end) ranges (atomicMin on run
+//     boundaries), which removes a separate sweep over the sorted pair list.
 // The digit histograms are produced by the kernels that generate the keys (preprocess /
-// binning), so a pass reads each pair exactly once: 16 B of HBM traffic per pair per pass.
+// binning), so a pass reads each pair exactly once: 16 B of traffic per pair per pass.
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
@@ -21,15 +32,50 @@ namespace ws {
 namespace {
 
 constexpr int WARPS = SORT_THREADS / 32;
+struct LbState { uint32_t excl; bool done; };
 
+// Walk one level of status words from row p down to row lo (nearest predecessor first).
+// `col` already points at this thread's bin column.  Up to four relaxed loads are issued per
+// step (they are independent), then consumed in order; an unpublished word restarts the step.
+// Rows below lo end the level; when `below_is_prefix` they count as "inclusive prefix 0".
+__device__ __forceinline__ void lookback_level(const uint32_t *col, int p, int lo, bool below_is_prefix,
+                                               LbState &st, uint32_t *err)
+{
+    uint32_t spins = 0;
+    while (!st.done) {
+        if (p < lo) { if (below_is_prefix) st.done = true; return; }
+        const int n = p - lo;                                  // extra rows available beyond p
+        const uint32_t s0 = ld_relaxed(col + (size_t)p * 256u);
+        const uint32_t s1 = (n >= 1) ? ld_relaxed(col + (size_t)(p - 1) * 256u) : 0u;
+        const uint32_t s2 = (n >= 2) ? ld_relaxed(col + (size_t)(p - 2) * 256u) : 0u;
+        const uint32_t s3 = (n >= 3) ? ld_relaxed(col + (size_t)(p - 3) * 256u) : 0u;
+        if ((s0 >> LB_FLAG_SHIFT) == 0u) {                     // nearest one not published yet: poll again
+            if (++spins > SPIN_LIMIT) { if (err) atomicOr(err, 1u); st.done = true; }
+            continue;
+        }
+        st.excl += s0 & LB_VALUE_MASK; --p;
+        if ((s0 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
+        if (n < 1 || (s1 >> LB_FLAG_SHIFT) == 0u) continue;
+        st.excl += s1 & LB_VALUE_MASK; --p;
+        if ((s1 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
+        if (n < 2 || (s2 >> LB_FLAG_SHIFT) == 0u) continue;
+        st.excl += s2 & LB_VALUE_MASK; --p;
+        if ((s2 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
+        if (n < 3 || (s3 >> LB_FLAG_SHIFT) == 0u) continue;
+        st.excl += s3 & LB_VALUE_MASK; --p;
+        if ((s3 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
+    }
+}
+
+template <bool EMIT_RANGES>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(SortPassArgs a)
 {
-    __shared__ uint32_t s_keys[SORT_PART];
+    __shared__ uint32_t s_keys[SORT_PART];      // during ranking the first 8 KB double as the peer masks
     __shared__ uint32_t s_vals[SORT_PART];
     __shared__ uint32_t s_whist[WARPS][256];
     __shared__ uint32_t s_binstart[256];      // first local position of each bin in the partition
-    __shared__ uint32_t s_gbase[256];         // global position of local position 0 of each bin, minus binstart
+    __shared__ uint32_t s_gbase[256];         // global position of local position 0, per bin
     __shared__ uint32_t s_scan[WARPS];
     __shared__ uint32_t s_part;
 
@@ -65,42 +111,51 @@ onesweep_pass_kernel(SortPassArgs a)
         if (part >= nparts) break;
         const uint32_t base = part * SORT_PART;
         const uint32_t nvalid = (n - base < (uint32_t)SORT_PART) ? (n - base) : (uint32_t)SORT_PART;
+        const bool full = nvalid == (uint32_t)SORT_PART;
 
-        // ---- load, warp-striped: warp w owns [base + w*512, +512), item i of lane l = i*32 + l
-        uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
+        // ---- load keys, warp-striped: warp w owns [base + w*512, +512), item i of lane l = i*32 + l
+        uint32_t key[SORT_ITEMS];
         const uint32_t wbase = warp * (32u * SORT_ITEMS);
-        if (nvalid == (uint32_t)SORT_PART) {
+        if (full) {
 #pragma unroll
             for (int i = 0; i < SORT_ITEMS; i++) key[i] = a.keys_in[base + wbase + i * 32u + lane];
-#pragma unroll
-            for (int i = 0; i < SORT_ITEMS; i++) val[i] = a.vals_in[base + wbase + i * 32u + lane];
         } else {
 #pragma unroll
             for (int i = 0; i < SORT_ITEMS; i++) {
                 const uint32_t li = wbase + i * 32u + lane;
                 key[i] = (li < nvalid) ? a.keys_in[base + li] : 0xffffffffu;   // pads rank last (radix_sort.wgsl:79)
-                val[i] = (li < nvalid) ? a.vals_in[base + li] : 0u;
             }
         }
 #pragma unroll
-        for (int i = 0; i < WARPS; i++) s_whist[i][tid] = 0u;
+        for (int i = 0; i < WARPS; i++) { s_whist[i][tid] = 0u; s_keys[i * 256 + tid] = 0u; }
         __syncthreads();
 
-        // ---- rank inside the warp: match peers with the same digit, leader bumps the warp counter
-        uint32_t rank[SORT_ITEMS];
+        // ---- rank inside the warp: peers via atomicOr masks, running count via the lowest peer
+        uint32_t rank2[SORT_ITEMS / 2];       // two 16-bit ranks per register (a rank is < 512)
+        {
+            uint32_t *wh = s_whist[warp];
+            uint32_t *wm = s_keys + warp * 256u;          // this warp's 256 peer masks (all zero between items)
+            const uint32_t lanebit = 1u << lane;
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; i++) {
-            const uint32_t d = (key[i] >> shift) & 255u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if ((int)lane == leader) old = atomicAdd(&s_whist[warp][d], (uint32_t)__popc(peers));
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[i] = old + __popc(peers & lanemask_lt());
+            for (int i = 0; i < SORT_ITEMS; i++) {
+                const uint32_t d = (key[i] >> shift) & 255u;
+                atomicOr(&wm[d], lanebit);
+                __syncwarp();
+                const uint32_t peers = wm[d];
+                const uint32_t old = wh[d];               // same value for all peers (broadcast read)
+                __syncwarp();
+                if ((peers & (lanebit - 1u)) == 0u) {     // lowest peer: advance the counter, clear the mask
+                    wh[d] = old + (uint32_t)__popc(peers);
+                    wm[d] = 0u;
+                }
+                const uint32_t rk = old + (uint32_t)__popc(peers & (lanebit - 1u));
+                if (i & 1) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
+                __syncwarp();
+            }
         }
         __syncthreads();
 
-        // ---- per bin (thread tid = bin): scan over warps, publish, look back
+        // ---- per bin (thread tid = bin): scan over warps, publish the partition's aggregate
         uint32_t total = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++) {
@@ -109,8 +164,20 @@ onesweep_pass_kernel(SortPassArgs a)
             total += c;
         }
         uint32_t *st = a.status + (size_t)part * 256u + tid;
-        if (part == 0u) st_relaxed(st, LB_PREFIX | total);
-        else st_relaxed(st, LB_AGGREGATE | total);
+        st_relaxed(st, (part == 0u ? LB_PREFIX : LB_AGGREGATE) | total);
+
+        // values are needed only for the reorder: issue their loads now
+        uint32_t val[SORT_ITEMS];
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < SORT_ITEMS; i++) val[i] = a.vals_in[base + wbase + i * 32u + lane];
+        } else {
+#pragma unroll
+            for (int i = 0; i < SORT_ITEMS; i++) {
+                const uint32_t li = wbase + i * 32u + lane;
+                val[i] = (li < nvalid) ? a.vals_in[base + li] : 0u;
+            }
+        }
 
         // block exclusive scan of `total` over bins -> first local position of each bin
         uint32_t binstart;
@@ -122,42 +189,40 @@ onesweep_pass_kernel(SortPassArgs a)
                 if ((int)lane >= o) incl += t;
             }
             if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
+            __syncthreads();                                   // also: every warp is done with the peer masks in s_keys
             uint32_t woff = 0;
 #pragma unroll
             for (int w = 0; w < WARPS; w++) if (w < (int)warp) woff += s_scan[w];
             binstart = woff + incl - total;
         }
-
-        uint32_t excl = 0;
-        if (part > 0u) {
-            int64_t p = (int64_t)part - 1;
-            uint32_t spins = 0;
-            for (;;) {
-                const uint32_t s = ld_relaxed(a.status + (size_t)p * 256u + tid);
-                const uint32_t f = s >> LB_FLAG_SHIFT;
-                if (f == 0u) {                              // predecessor not published yet: spin
-                    if (++spins > SPIN_LIMIT) { if (a.err) atomicOr(a.err, 1u); break; }
-                    continue;
-                }
-                excl += s & LB_VALUE_MASK;
-                if (f == 2u) break;
-                --p;
-            }
-            st_relaxed(st, LB_PREFIX | (excl + total));
-        }
         s_binstart[tid] = binstart;
-        s_gbase[tid] = g_excl + excl - binstart;            // wraps mod 2^32 by design
         __syncthreads();
 
-        // ---- reorder in shared memory
+        // ---- reorder in shared memory (needs only block-local information); meanwhile the
+        //      predecessors get time to publish, which shortens the look-back below
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; i++) {
             const uint32_t d = (key[i] >> shift) & 255u;
-            const uint32_t pos = s_binstart[d] + s_whist[warp][d] + rank[i];
+            const uint32_t pos = s_binstart[d] + s_whist[warp][d] + ((rank2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
             s_keys[pos] = key[i];
             s_vals[pos] = val[i];
         }
+
+        // ---- two-level decoupled look-back
+        LbState lb; lb.excl = 0; lb.done = (part == 0u);
+        {
+            const uint32_t grp = part / SORT_LB_GROUP;
+            const bool leader = (part % SORT_LB_GROUP) == SORT_LB_GROUP - 1u;
+            lookback_level(a.status + tid, (int)part - 1, (int)(grp * SORT_LB_GROUP), grp == 0u, lb, a.err);   // inside the group
+            uint32_t *gst = a.gstatus + (size_t)grp * 256u + tid;
+            if (leader) st_relaxed(gst, (lb.done ? LB_PREFIX : LB_AGGREGATE) | ((lb.excl + total) & LB_VALUE_MASK));
+            if (!lb.done) {
+                lookback_level(a.gstatus + tid, (int)grp - 1, 0, true, lb, a.err);                            // over earlier groups
+                if (leader) st_relaxed(gst, LB_PREFIX | ((lb.excl + total) & LB_VALUE_MASK));
+            }
+            if (part > 0u) st_relaxed(st, LB_PREFIX | ((lb.excl + total) & LB_VALUE_MASK));
+        }
+        s_gbase[tid] = g_excl + lb.excl - binstart;            // wraps mod 2^32 by design
         __syncthreads();
 
         // ---- write out: consecutive threads write consecutive addresses within a bin run
@@ -169,6 +234,15 @@ onesweep_pass_kernel(SortPassArgs a)
                 const uint32_t g = s_gbase[(kk >> shift) & 255u] + i;
                 a.keys_out[g] = kk;
                 a.vals_out[g] = s_vals[i];
+                if (EMIT_RANGES) {
+                    // The output of the last pass is fully sorted, so equal keys are contiguous in
+                    // global memory.  Inside a bin run local neighbours are global neighbours; at
+                    // run boundaries the global neighbour is unknown, hence min/max via atomics.
+                    const bool first = (i == 0u) || (s_keys[i - 1u] != kk);
+                    const bool last = (i == nvalid - 1u) || (s_keys[i + 1u] != kk);
+                    if (first) atomicMin(&a.ranges[kk].x, g);
+                    if (last) atomicMin(&a.ranges[kk].y, ~(g + 1u));
+                }
             }
         }
         __syncthreads();
@@ -182,20 +256,14 @@ sort_histogram_kernel(const uint32_t *__restrict__ keys, const uint32_t *n_ptr, 
                       uint32_t *hist, int passes)
 {
     __shared__ uint32_t s_hist[4 * 256];
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned tid = threadIdx.x;
     for (unsigned i = tid; i < 4u * 256u; i += 256u) s_hist[i] = 0u;
     __syncthreads();
     uint32_t n = *n_ptr;
     if (n > n_cap) n = n_cap;
-    const uint32_t nround = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * 256u + tid; i < nround; i += gridDim.x * 256u) {
-        const bool ok = i < n;
-        const uint32_t k = ok ? keys[i] : 0u;
-        for (int d = 0; d < passes; d++) {
-            const uint32_t dig = (k >> (8 * d)) & 255u;
-            const unsigned peers = __match_any_sync(0xffffffffu, ok ? dig : 0xffffffffu);
-            if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[d * 256 + dig], (uint32_t)__popc(peers));
-        }
+    for (uint32_t i = blockIdx.x * 256u + tid; i < n; i += gridDim.x * 256u) {
+        const uint32_t k = keys[i];
+        for (int d = 0; d < passes; d++) atomicAdd(&s_hist[d * 256 + ((k >> (8 * d)) & 255u)], 1u);   // shared atomics w/o return: ~120 G warp-ops/s
     }
     __syncthreads();
     for (unsigned i = tid; i < (unsigned)passes * 256u; i += 256u) {
@@ -208,14 +276,17 @@ sort_histogram_kernel(const uint32_t *__restrict__ keys, const uint32_t *n_ptr, 
 
 cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t stream)
 {
-    onesweep_pass_kernel<<<grid, SORT_THREADS, 0, stream>>>(a);
+    if (a.ranges) onesweep_pass_kernel<true><<<grid, SORT_THREADS, 0, stream>>>(a);
+    else onesweep_pass_kernel<false><<<grid, SORT_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 int sort_pass_blocks_per_sm()
 {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, onesweep_pass_kernel, SORT_THREADS, 0);
+    int nb = 0, nb2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, onesweep_pass_kernel<false>, SORT_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, onesweep_pass_kernel<true>, SORT_THREADS, 0);
+    if (nb2 < nb) nb = nb2;
     return nb > 0 ? nb : 1;
 }
 

@@ -11,6 +11,7 @@ struct FrameCounters;
 // ---- stage 1 -----------------------------------------------------------------
 struct PreprocessArgs {
     const uint8_t *gaussians;     // N x 28 B (raw) / 24 B (compressed), padded to a multiple of 256 records
+    const float *xyz;             // N x 3 f32: position plane for the count kernel (derived at upload)
     const uint8_t *sh_coefs;      // raw: N x 96 B; compressed: i8 entries
     const uint8_t *covars;        // compressed only: 12 B per entry
     const FrameUniforms *uniforms;
@@ -18,18 +19,19 @@ struct PreprocessArgs {
     uint32_t *depth_keys;         // out: V
     uint32_t *slot_vals;          // out: V (iota payload)
     uint2 *rects;                 // out: V x {x0 | y0<<16, w | h<<16}
-    uint32_t *scan_status;        // ceil(N/256) look-back words (zeroed per frame)
-    uint32_t *ticket;             // zeroed per frame
+    uint32_t *part_counts;        // ceil(N/256): survivors per partition (count kernel)
+    uint32_t *part_bases;         // ceil(N/256): exclusive scan of part_counts (scan kernel)
     uint32_t *hist;               // 4 x 256 depth-key digit histograms (zeroed per frame)
     FrameCounters *counters;
 };
-cudaError_t launch_preprocess(const PreprocessArgs &a, bool compressed, int grid, cudaStream_t stream);
+cudaError_t launch_preprocess(const PreprocessArgs &a, bool compressed, int grid_count, int grid_main, cudaStream_t stream);
 int preprocess_blocks_per_sm(bool compressed);
 
 // ---- onesweep radix sort of (u32 key, u32 value) pairs ---------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_PART = SORT_THREADS * SORT_ITEMS;   // 4096 pairs per partition
+constexpr unsigned SORT_LB_GROUP = 16;                 // partitions per look-back group (two-level look-back)
 
 struct SortPassArgs {
     const uint32_t *keys_in, *vals_in;
@@ -37,10 +39,12 @@ struct SortPassArgs {
     const uint32_t *n_ptr;        // device: number of pairs (clamped to n_cap)
     uint32_t n_cap;
     uint32_t *status;             // [ceil(n_cap/4096)][256] look-back words, zeroed before the pass
+    uint32_t *gstatus;            // [ceil(parts/16)][256] group-level look-back words, zeroed before the pass
     uint32_t *ticket;             // zeroed before the pass
     const uint32_t *hist;         // 256 digit counts of this pass (over the first min(*n_ptr,n_cap) keys)
     uint32_t shift;               // digit = (key >> shift) & 255
     uint32_t *err;                // optional error word (bit 0: look-back watchdog)
+    uint2 *ranges;                // last tile-id pass only: per-tile {begin, ~end}, pre-filled with 0xff; else NULL
 };
 cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t stream);
 int sort_pass_blocks_per_sm();
@@ -56,22 +60,18 @@ struct BinningArgs {
     FrameCounters *counters;      // reads num_visible, writes num_pairs / pair_overflow
     uint32_t *pair_tiles;         // out: P tile ids
     uint32_t *pair_slots;         // out: P slots
-    uint32_t *scan_status;        // ceil(N/256) look-back words (zeroed per frame)
-    uint32_t *ticket;
+    uint32_t *part_counts;        // ceil(N/1024): pairs per partition (count kernel)
+    uint32_t *part_bases;         // ceil(N/1024): exclusive scan (scan kernel)
     uint32_t *hist;               // 4 x 256 tile-id digit histograms (zeroed per frame)
 };
-cudaError_t launch_binning(const BinningArgs &a, int grid, cudaStream_t stream);
+cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand, cudaStream_t stream);
 int binning_blocks_per_sm();
-
-// per-tile [begin,end) over the sorted pair list; ranges must be zeroed by the caller
-cudaError_t launch_tile_ranges(const uint32_t *pair_tiles, const FrameCounters *counters, uint32_t pair_cap,
-                               uint2 *ranges, int grid, cudaStream_t stream);
 
 // ---- stage 3 -----------------------------------------------------------------------
 struct CompositeArgs {
     const uint32_t *splats;       // V x 5 u32
     const uint32_t *pair_slots;   // sorted
-    const uint2 *ranges;          // T
+    const uint2 *ranges;          // T x {begin, ~end}; untouched tiles hold 0xffffffff in both words
     const FrameUniforms *uniforms;
     void *dst;                    // device frame
     uint32_t row_pitch;           // bytes
