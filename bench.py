@@ -264,7 +264,7 @@ def run_ours(args):
     V, P = float(np.mean(counts["V"])), float(np.mean(counts["P"]))
     N = cloud["num_points"]
     T = ((W + 15) // 16) * ((H + 15) // 16)
-    depth_passes = 3 if cloud["compressed"] else 4
+    depth_passes = 4
     tile_passes = 3 if T > 65536 else (2 if T > 256 else 1)
     peak, peak_src, sm_max = measured_peaks()
 

@@ -231,3 +231,53 @@ def test_determinism(ws, ctx):
     pos, rot = ws.synth.orbit_camera(120.0)
     imgs = [_frame(ws, ctx, cloud, pos, rot, 512, 288)[2] for _ in range(3)]
     assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+
+
+# ---- compressed (npz / c3dgs) layout: BASELINE.json configs[3] -----------------------------------
+def _check_compressed(ws, orc, ctx, cloud, pos, rot, W, H, **kw):
+    """preprocess_compressed.wgsl: exact visible set and keys; halves within 1 f16 ulp (expf of the
+    scale factor differs between glibc and CUDA by an ulp, which propagates into the axes); the
+    image is compared against the oracle composited over the CUDA splats' own order."""
+    from helpers import f16_ordered
+    r, pc, img, (fovx, fovy) = _frame(ws, ctx, cloud, pos, rot, W, H, **kw)
+    zn, zf = orc.fit_near_far(pos, cloud["aabb_min"], cloud["aabb_max"])
+    cam = orc.camera_uniform(pos, rot, fovx, fovy, zn, zf, W, H)
+    st = orc.render_settings(cloud, **kw)
+    osplats, okeys, _ = orc.preprocess(cloud, cam, st)
+    V = len(okeys)
+    assert r.num_visible_points() == V
+    splats = r.read_buffer(ws.BUF_SPLATS_2D)
+    assert np.array_equal(r.read_buffer(ws.BUF_DEPTH_KEYS), okeys)         # 24-bit integer keys: exact
+    d = np.abs(f16_ordered(splats) - f16_ordered(osplats))
+    assert d[:, 4:].max() <= 1                                             # centre, colour, opacity
+    a = splats.view(np.float16).astype(np.float64); b = osplats.view(np.float16).astype(np.float64)
+    for sl in (slice(0, 2), slice(2, 4)):                                  # axes as vectors (see test_oracle)
+        na = np.linalg.norm(b[:, sl] * [W, H], axis=1)
+        err = np.linalg.norm((a[:, sl] - b[:, sl]) * [W, H], axis=1)
+        assert (err <= 4e-3 * na + 1e-3).all()
+    sk, order = orc.sort_pairs(okeys, np.arange(V, dtype=np.uint32))
+    assert np.array_equal(r.read_buffer(ws.BUF_SORTED_KEYS), sk)
+    assert np.array_equal(r.read_buffer(ws.BUF_SORTED_INDICES), order)
+    ref, sens = orc.composite(splats, order, W, H, want_sens=True)          # same splats, oracle compositor
+    dd, ok = image_close(img, ref, sens)
+    assert ok.all(), "image: %d px outside tolerance, max %.3g" % ((~ok).sum(), dd.max())
+    # and against the all-oracle frame with the looser bound the 1-ulp splat differences allow
+    ref2 = orc.composite(osplats, order, W, H)
+    assert np.abs(img - ref2).max() < 2e-2 and np.abs(img - ref2).mean() < 2e-4
+    return r
+
+
+@pytest.mark.parametrize("identity", [False, True])
+def test_compressed_layout(ws, orc, ctx, identity):
+    cloud = ws.synth.make_cloud_compressed(30000, 21, codebook=512, identity_index=identity)
+    pos, rot = ws.synth.orbit_camera(75.0)
+    r = _check_compressed(ws, orc, ctx, cloud, pos, rot, 480, 270)
+    assert r.stats()["num_pairs"] > 0
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_compressed_lower_degree_files(ws, orc, ctx, deg):
+    """the SH stride of a compressed cloud depends on the FILE's degree (preprocess_compressed.wgsl:147-153)"""
+    cloud = ws.synth.make_cloud_compressed(8000, 22, sh_deg=deg, codebook=256)
+    pos, rot = ws.synth.orbit_camera(200.0)
+    _check_compressed(ws, orc, ctx, cloud, pos, rot, 320, 200, max_sh_deg=deg)

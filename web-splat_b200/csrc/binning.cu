@@ -93,42 +93,46 @@ bin_count_kernel(BinningArgs a)
 __global__ void __launch_bounds__(1024)
 bin_scan_kernel(BinningArgs a)
 {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_total;
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ uint32_t total_out;
     const uint32_t V = a.counters->num_visible;
     const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
-    uint32_t carry = 0;
-    for (uint32_t b = 0; b < nparts; b += 1024u) {
-        const uint32_t i = b + tid;
-        const uint32_t c = (i < nparts) ? a.part_counts[i] : 0u;
-        uint32_t incl = c;
+    const uint32_t *counts = a.part_counts;
+    uint32_t *bases = a.part_bases;
+    __shared__ uint32_t s_w[32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t per = (nparts + 1023u) / 1024u;            // contiguous elements per thread
+    const uint32_t lo = tid * per, hi = (lo + per < nparts) ? lo + per : nparts;
+    uint32_t sum = 0;
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = s_w[lane];
+        uint32_t vi = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
+            uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+            if ((int)lane >= o) vi += t;
         }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t v = s_w[lane];
-            uint32_t vi = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
-                if ((int)lane >= o) vi += t;
-            }
-            s_w[lane] = vi - v;
-            if (lane == 31) s_total = vi;
-        }
-        __syncthreads();
-        if (i < nparts) a.part_bases[i] = carry + s_w[warp] + incl - c;
-        carry += s_total;
-        __syncthreads();
+        s_w[lane] = vi - v;                                   // exclusive offset of each warp
+        if (lane == 31) total_out = vi;
     }
-    if (tid == 0) {
-        a.counters->num_pairs = carry;
-        a.counters->pair_overflow = (carry > a.uniforms->pair_capacity) ? 1u : 0u;
+    __syncthreads();
+    uint32_t run = s_w[warp] + incl - sum;
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t c = counts[i]; bases[i] = run; run += c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t P = (nparts > 0u) ? total_out : 0u;
+        a.counters->num_pairs = P;
+        a.counters->pair_overflow = (P > a.uniforms->pair_capacity) ? 1u : 0u;
     }
 }
 
@@ -182,7 +186,8 @@ bin_expand_kernel(BinningArgs a)
 #pragma unroll
         for (int j = 0; j < BIN_SPT; j++) {
             s_info[tid * BIN_SPT + j] = make_uint4(excl[j], r.xy[j], r.slot[j], r.w[j]);
-            s_magic[tid * BIN_SPT + j] = (r.w[j] > 1u) ? (0xffffffffu / r.w[j] + 1u) : 0u;
+            s_magic[tid * BIN_SPT + j] = (r.w[j] > 1u) ? __float2uint_ru(__fdiv_ru(4294967296.f, (float)r.w[j])) : 0u;
+            // m >= 2^32/w with m*w - 2^32 <= w + 512: floor(t/w) == umulhi(t, m) for every t < 2^20, w <= 1024 (viewport <= 16384)
         }
 
         for (uint32_t c0 = 0; c0 < total; c0 += BIN_CAP) {

@@ -368,8 +368,9 @@ extern "C" ws_status ws_renderer_create(ws_context *ctx, ws_format fmt, uint32_t
     r->grid_pre = ctx->sm_count * preprocess_blocks_per_sm(r->compressed);
     r->grid_sort = ctx->sm_count * sort_pass_blocks_per_sm();
     r->grid_bin = ctx->sm_count * binning_blocks_per_sm();
-    // 24-bit integer keys in the compressed shader (preprocess_compressed.wgsl:325): 3 digit passes
-    r->depth_passes = r->compressed ? 3 : 4;
+    // 4 digit passes for both layouts: the compressed shader's "24-bit" key
+    // (preprocess_compressed.wgsl:325) exceeds 0xffffff whenever clip.z < znear
+    r->depth_passes = 4;
     memset(&r->h_uniforms, 0, sizeof r->h_uniforms);
     *out = r;
     return WS_OK;

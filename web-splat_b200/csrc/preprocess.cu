@@ -15,9 +15,9 @@
 //    profiles/): its look-back serialised the prefetch pipeline.  The price is re-reading xyz:
 //    +12 B on top of 124 B per Gaussian;
 //  * MAIN is software-pipelined: partitions are assigned round-robin, the 28-B (24-B) AoS
-//    records of partition k+2 and -- when at least half of it survives -- its 24-KB SH block
+//    records of partition k+1 and -- when at least half of it survives -- its 24-KB SH block
 //    are fetched by cp.async.bulk (TMA engine, UBLKCP) into shared-memory rings while
-//    partition k is being computed; ~100 KB per SM are in flight, HBM sees only full bursts;
+//    partition k is being computed; 3 CTAs x 31 KB per SM are in flight, HBM sees only full bursts;
 //    sparse partitions fetch SH with three 256-bit loads per surviving lane instead
 //    (one full 32-B sector per request);
 //  * records are read from shared memory at a conflict-free 7-word (6-word: 2-way) stride;
@@ -322,7 +322,7 @@ count_kernel(PreprocessArgs a)
     const FrameUniforms &U = s_u;
     const uint32_t n = U.num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
-    constexpr int NDIG = COMPRESSED ? 3 : 4;
+    constexpr int NDIG = 4;
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         const uint32_t idx = part * PP_THREADS + tid;
         bool keep = false;
@@ -354,44 +354,45 @@ __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, const FrameUniforms *uniforms,
             FrameCounters *counters)
 {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_total;
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ uint32_t total_out;
     const uint32_t n = uniforms->num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
-    uint32_t carry = 0;
-    for (uint32_t b = 0; b < nparts; b += 1024u) {
-        const uint32_t i = b + tid;
-        const uint32_t c = (i < nparts) ? counts[i] : 0u;
-        uint32_t incl = c;
+    __shared__ uint32_t s_w[32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t per = (nparts + 1023u) / 1024u;            // contiguous elements per thread
+    const uint32_t lo = tid * per, hi = (lo + per < nparts) ? lo + per : nparts;
+    uint32_t sum = 0;
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = s_w[lane];
+        uint32_t vi = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
+            uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+            if ((int)lane >= o) vi += t;
         }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t v = s_w[lane];
-            uint32_t vi = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
-                if ((int)lane >= o) vi += t;
-            }
-            s_w[lane] = vi - v;                       // exclusive offset of each warp
-            if (lane == 31) s_total = vi;             // chunk total
-        }
-        __syncthreads();
-        if (i < nparts) bases[i] = carry + s_w[warp] + incl - c;
-        carry += s_total;
-        __syncthreads();
+        s_w[lane] = vi - v;                                   // exclusive offset of each warp
+        if (lane == 31) total_out = vi;
     }
-    if (tid == 0) counters->num_visible = carry;
+    __syncthreads();
+    uint32_t run = s_w[warp] + incl - sum;
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t c = counts[i]; bases[i] = run; run += c; }
+    __syncthreads();
+    if (threadIdx.x == 0) counters->num_visible = total_out;
 }
 
 // ---- (3) MAIN ---------------------------------------------------------------------------------
-constexpr int PP_STAGES = 3;                         // ring depth: records and SH of k+1, k+2 in flight
+constexpr int PP_STAGES = 2;                         // ring depth: records and SH of partition k+1 in flight while k is computed
 constexpr uint32_t PP_SH_BYTES = PP_THREADS * 96u;   // one partition's SH block
 constexpr uint32_t PP_SH_BULK_MIN = 128;             // bulk-stage the SH block when >= half the partition survives
 
@@ -411,7 +412,7 @@ struct PPSmem {
 };
 
 template <bool COMPRESSED>
-__global__ void __launch_bounds__(PP_THREADS, 2)
+__global__ void __launch_bounds__(PP_THREADS, 3)
 preprocess_kernel(PreprocessArgs a)
 {
     using L = PPSmem<COMPRESSED>;
@@ -457,14 +458,14 @@ preprocess_kernel(PreprocessArgs a)
         }
     };
 
-    if (tid == 0) { issue(0); issue(1); }
+    if (tid == 0) issue(0);
     uint32_t rpar = 0, spar = 0;                      // per-slot mbarrier phase parities (block-uniform)
 
     for (uint32_t k = 0;; k++) {
         const uint32_t part = part_of(k);
         if (part >= nparts) break;
         const uint32_t s = k % PP_STAGES;
-        if (tid == 0) issue(k + 2u);                  // slot (k+2)%3 was last read in iteration k-1 (trailing barrier)
+        if (tid == 0) issue(k + 1u);                  // slot (k+1)%2 was last read in iteration k-1 (trailing barrier)
 
         const bool bulk = uses_bulk_sh(part);
         mbar_wait(&s_rbar[s], (rpar >> s) & 1u); rpar ^= 1u << s;
