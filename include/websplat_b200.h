@@ -223,6 +223,32 @@ WS_API ws_status ws_sort_pairs_u32(ws_context *ctx, uint32_t *keys_device, uint3
 WS_API ws_status ws_sort_pairs_u32_host(ws_context *ctx, uint32_t *keys_host, uint32_t *payload_host,
                                         uint32_t n, uint32_t key_bits);
 
+/* ---- sharded rendering over the GPUs of one box (new: the reference is single-GPU) -----------
+ * One process per GPU.  Rank r uploads Gaussians [r*N/G, (r+1)*N/G) as its ws_pointcloud (with the
+ * GLOBAL aabb/center metadata) and owns a band of 16-pixel tile rows of the frame.  Per frame:
+ *   shard_begin     stage 1 on the local shard + routing counts; writes this rank's row of the
+ *                   G x G count matrix (G u32, DEVICE memory) to totals_row_device
+ *   [host layer]    all-gather the rows (NCCL), G*G u32 on every rank
+ *   shard_exchange  one kernel that stores every visible splat (20-B Splat, key, clipped tile
+ *                   rectangle) directly into the owning ranks' buffers through peer-mapped pointers
+ *   [host layer]    cross-rank barrier (e.g. a 4-byte NCCL all-reduce on the same stream)
+ *   shard_finish    depth sort, binning, tile sort on what this rank received
+ *   render_band     stage 3 for the rank's rows; the host layer gathers the bands.
+ * Records arrive in global Gaussian-index order, so the result is bit-identical to one GPU.
+ * Setup: shard_configure on every rank, exchange the 3x64-byte handles of shard_export (e.g.
+ * torch.distributed.all_gather), shard_import.  Buffers never move after configure. */
+WS_API ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, uint32_t world, uint64_t total_points,
+                                             uint32_t local_points, uint32_t width, uint32_t height);
+WS_API ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_3x64);
+WS_API ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_handles_world_x_3x64);
+WS_API ws_status ws_renderer_shard_begin(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
+                                         uint32_t *totals_row_device, void *cuda_stream);
+WS_API ws_status ws_renderer_shard_exchange(ws_renderer *r, const uint32_t *matrix_device, void *cuda_stream);
+WS_API ws_status ws_renderer_shard_finish(ws_renderer *r, const uint32_t *matrix_device, void *cuda_stream);
+WS_API ws_status ws_renderer_shard_band(const ws_renderer *r, uint32_t *first_row, uint32_t *num_rows);
+WS_API ws_status ws_renderer_render_band(ws_renderer *r, ws_pointcloud *pc, void *dst_rgba_device, size_t row_pitch_bytes,
+                                         const double clear[4], void *cuda_stream);
+
 /* ---- uniforms, for inspection (renderer.rs:125, 285) ------------------------
  * CameraUniform (272 B, src/renderer.rs:290-306) and SplattingArgsUniform
  * (80 B, src/renderer.rs:604-619) exactly as the reference would upload them. */

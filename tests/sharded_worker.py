@@ -1,0 +1,54 @@
+"""torchrun worker for tests/test_gpu_sharded.py: renders the same frames on G GPUs (sharded) and on
+one GPU (rank 0, plain path) and requires bit-identical images."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np                      # noqa: E402
+import torch                            # noqa: E402
+import torch.distributed as dist        # noqa: E402
+import websplat_b200 as ws              # noqa: E402
+from helpers import make_args, make_generic   # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = ws.Context(local)
+    ok = True
+    for n, W, H, fmt in ((60000, 800, 600, ws.FORMAT_RGBA32_FLOAT), (200000, 1200, 799, ws.FORMAT_RGBA16_FLOAT)):
+        cloud = ws.synth.make_cloud(n, 1234 + n)
+        shard = ws.shard_cloud(cloud, rank, world)
+        pc = ws.PointCloud.new(ctx, make_generic(ws, shard))
+        sh = ws.ShardedRenderer(ws, ctx, fmt, 3, False, pc, n, (W, H))
+        fovx, fovy = ws.synth.fov_for_viewport(W, H)
+        for az in (0.0, 95.0, 250.0):
+            pos, rot = ws.synth.orbit_camera(az)
+            args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
+            img = sh.frame(args, clear=(0.1, 0.2, 0.3, 0.5))
+            torch.cuda.synchronize()
+            if rank == 0:
+                full = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+                plain = ws.GaussianRenderer.new(ctx, fmt, 3, False)
+                plain.prepare(None, full, args)
+                ref = torch.empty_like(img)
+                plain.render(ref, full, (0.1, 0.2, 0.3, 0.5))
+                torch.cuda.synchronize()
+                same = torch.equal(ref, img)
+                ok = ok and same
+                print("n=%d %dx%d az=%.0f identical=%s V=%d" % (n, W, H, az, same, sh.stats()["num_visible"]), flush=True)
+            dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and int(flag.item()) == 1:
+        print("SHARDED_OK", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,8 @@ EXPORTED_SYMBOLS = [
     "ws_renderer_num_visible_points", "ws_renderer_stats", "ws_renderer_set_pair_capacity",
     "ws_renderer_set_timing", "ws_renderer_read_buffer", "ws_sort_pairs_u32", "ws_sort_pairs_u32_host",
     "ws_renderer_camera_uniform", "ws_renderer_settings_uniform", "ws_version",
+    "ws_renderer_shard_configure", "ws_renderer_shard_export", "ws_renderer_shard_import", "ws_renderer_shard_begin",
+    "ws_renderer_shard_exchange", "ws_renderer_shard_finish", "ws_renderer_shard_band", "ws_renderer_render_band",
 ]
 
 _lib = None
@@ -180,6 +182,14 @@ def lib():
         "ws_sort_pairs_u32_host": (i32, [vp, vp, vp, u32, u32]),
         "ws_renderer_camera_uniform": (i32, [vp, C.POINTER(f32 * 68)]),
         "ws_renderer_settings_uniform": (i32, [vp, vp]),
+        "ws_renderer_shard_configure": (i32, [vp, u32, u32, u64, u32, u32, u32]),
+        "ws_renderer_shard_export": (i32, [vp, vp]),
+        "ws_renderer_shard_import": (i32, [vp, vp]),
+        "ws_renderer_shard_begin": (i32, [vp, vp, C.POINTER(ws_splatting_args), vp, vp]),
+        "ws_renderer_shard_exchange": (i32, [vp, vp, vp]),
+        "ws_renderer_shard_finish": (i32, [vp, vp, vp]),
+        "ws_renderer_shard_band": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "ws_renderer_render_band": (i32, [vp, vp, vp, C.c_size_t, C.POINTER(C.c_double * 4), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -552,3 +562,4 @@ def sort_pairs_host(ctx, keys, payload, key_bits=32):
 
 
 from . import synth  # noqa: E402,F401
+from .distributed import ShardedRenderer, shard_cloud, tile_row_bands  # noqa: E402,F401

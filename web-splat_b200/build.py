@@ -24,6 +24,7 @@ UNITS = {
     "radix_sort.cu": [],
     "binning.cu": [],
     "composite.cu": [],
+    "shard.cu": [],
     "capi.cu": [],
 }
 HEADERS = ["ws_device.cuh", "ws_kernels.h", os.path.join("..", "..", "include", "websplat_b200.h")]

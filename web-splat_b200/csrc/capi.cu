@@ -281,6 +281,20 @@ extern "C" int32_t ws_pointcloud_dilation_kernel_size(const ws_pointcloud *pc, f
 enum { EV_START = 0, EV_PRE, EV_DSORT, EV_BIN, EV_TSORT, EV_BLEND0, EV_BLEND1, EV_COUNT };
 enum { TK_PRE = 0, TK_BIN = 1, TK_DSORT = 2, TK_TSORT = 6 };
 
+struct ShardState {
+    uint32_t rank = 0, world = 0;              // world == 0: not sharded
+    uint32_t width = 0, height = 0;
+    uint32_t band_y0[9] = {};                  // tile-row bands: rank d owns rows [band_y0[d], band_y0[d+1])
+    uint32_t recv_cap = 0, local_cap = 0;
+    uint32_t *l_splats = nullptr, *l_keys = nullptr, *l_vals = nullptr; uint2 *l_rects = nullptr;   // stage-1 output of the local shard
+    uint32_t *d_route = nullptr; size_t route_words = 0;
+    uint32_t *part_band_counts = nullptr, *part_band_bases = nullptr, *hist_dummy = nullptr;
+    uint32_t *peer_splats[8] = {}, *peer_keys[8] = {}; uint2 *peer_rects[8] = {};
+    bool opened[8] = {};
+    bool imported = false;
+    int phase = 0;
+};
+
 struct ws_renderer {
     ws_context *ctx;
     ws_format format;
@@ -321,8 +335,10 @@ struct ws_renderer {
     bool ev_ok = false;
     cudaStream_t last_stream = nullptr;
     uint32_t last_n = 0;
+    ShardState shard;
 };
 
+static void free_shard(ws_renderer *r);
 static void free_sort_stuff(ws_renderer *r)
 {
     cudaFree(r->d_scratch); r->d_scratch = nullptr;
@@ -341,6 +357,7 @@ extern "C" void ws_renderer_destroy(ws_renderer *r)
 {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
+    free_shard(r);
     free_sort_stuff(r);
     cudaFree(r->d_uniforms); cudaFree(r->d_ranges); cudaFree(r->d_frame);
     if (r->ev_ok) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(r->ev[i]);
@@ -404,6 +421,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
     }
     const uint32_t pair_cap = (uint32_t)want_pairs;
     if (!(r->d_scratch && r->n_cap == n && r->pair_cap == pair_cap)) {
+        if (r->shard.world > 0 && r->d_scratch) return fail(WS_ERR_INVALID_ARGUMENT, "sharded renderer: capacities are fixed by ws_renderer_shard_configure");
         free_sort_stuff(r);
         const size_t nn = n ? n : 1;
         const size_t parts256 = (nn + 255) / 256;
@@ -471,7 +489,7 @@ static void build_settings_uniform(const ws_splatting_args *a, const ws_pointclo
     s->scene_extend = ext;
 }
 
-extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, void *cuda_stream)
+static ws_status validate_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args)
 {
     if (!r || !pc || !args) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (pc->compressed != r->compressed) return fail(WS_ERR_MISMATCH, "renderer/point cloud 'compressed' mismatch");
@@ -480,14 +498,17 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     if (args->viewport[0] > 16384 || args->viewport[1] > 16384) return fail(WS_ERR_UNSUPPORTED, "viewport larger than 16384");
     if (args->max_sh_deg > 3) return fail(WS_ERR_INVALID_ARGUMENT, "max_sh_deg > 3");
     if (r->compressed && args->max_sh_deg > r->sh_deg) return fail(WS_ERR_INVALID_ARGUMENT, "max_sh_deg exceeds the compressed cloud's degree");
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
-    CU(cudaSetDevice(r->ctx->device));
+    return WS_OK;
+}
 
+// uniforms + per-frame clears (everything before stage 1)
+static ws_status begin_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, uint32_t capacity_points, cudaStream_t stream)
+{
     const uint32_t W = args->viewport[0], H = args->viewport[1];
     const uint32_t tx = (W + TILE - 1) / TILE, ty = (H + TILE - 1) / TILE;
     const uint32_t tiles = tx * ty;
     r->prepared = false; r->rendered = false;
-    ws_status st = ensure_capacity(r, pc->n, tiles);
+    ws_status st = ensure_capacity(r, capacity_points, tiles);
     if (st != WS_OK) return st;
 
     FrameUniforms &U = r->h_uniforms;
@@ -502,19 +523,13 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     CU(cudaMemcpyAsync(r->d_uniforms, &U, sizeof U, cudaMemcpyHostToDevice, stream));
     CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
     CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)tiles * 8, stream));    // {begin, ~end} identities for atomicMin
+    return WS_OK;
+}
 
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
-    {   // ---- stage 1
-        PreprocessArgs a;
-        a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
-        a.uniforms = r->d_uniforms;
-        a.splats = r->d_splats; a.depth_keys = r->d_keys[0]; a.slot_vals = r->d_vals[0]; a.rects = r->d_rects;
-        a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
-        a.hist = r->d_hist_depth; a.counters = r->d_counters;
-        CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
-    }
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
-    {   // ---- stage 2a: depth passes on the V visible splats
+// stage 2: depth passes on the V visible splats, tile binning, tile-id passes (+ ranges)
+static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
+{
+    {   // ---- stage 2a
         const size_t sparts_n = ((size_t)(r->n_cap ? r->n_cap : 1) + SORT_PART - 1) / SORT_PART;
         int src = 0;
         for (int p = 0; p < r->depth_passes; p++) {
@@ -564,17 +579,226 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
         r->tile_out = src;
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_TSORT], stream));
+    return WS_OK;
+}
 
+extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, void *cuda_stream)
+{
+    ws_status st = validate_frame(r, pc, args);
+    if (st != WS_OK) return st;
+    if (r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is configured for sharding: use ws_renderer_shard_begin/exchange/finish");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    st = begin_frame(r, pc, args, pc->n, stream);
+    if (st != WS_OK) return st;
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
+    {   // ---- stage 1
+        PreprocessArgs a;
+        a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
+        a.uniforms = r->d_uniforms;
+        a.splats = r->d_splats; a.depth_keys = r->d_keys[0]; a.slot_vals = r->d_vals[0]; a.rects = r->d_rects;
+        a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
+        a.hist = r->d_hist_depth; a.counters = r->d_counters;
+        CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
+    }
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
+    st = enqueue_stage2(r, stream);
+    if (st != WS_OK) return st;
     r->prepared = true;
     r->last_stream = stream;
     r->last_n = pc->n;
     return WS_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// Sharded (multi-GPU) frame: SURVEY.md 8(e), csrc/shard.cu.  One process per GPU; the host layer
+// (torch.distributed / NCCL) moves the G x G count matrix and provides the barrier.
+static void free_shard(ws_renderer *r)
+{
+    ShardState &s = r->shard;
+    for (int p = 0; p < 8; p++) {
+        if (s.opened[p]) {
+            cudaIpcCloseMemHandle(s.peer_splats[p]); cudaIpcCloseMemHandle(s.peer_keys[p]); cudaIpcCloseMemHandle(s.peer_rects[p]);
+            s.opened[p] = false;
+        }
+    }
+    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route);
+    s = ShardState();
+}
+
+extern "C" ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, uint32_t world, uint64_t total_points,
+                                                 uint32_t local_points, uint32_t width, uint32_t height)
+{
+    if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
+    if (world < 1 || world > 8 || rank >= world) return fail(WS_ERR_INVALID_ARGUMENT, "need 1 <= world <= 8 and rank < world");
+    if (total_points >= (1ull << 30) || width == 0 || height == 0) return fail(WS_ERR_INVALID_ARGUMENT, "bad total_points / viewport");
+    CU(cudaSetDevice(r->ctx->device));
+    free_shard(r);
+    free_sort_stuff(r);
+    ShardState &s = r->shard;
+    s.rank = rank; s.world = world; s.width = width; s.height = height;
+    s.recv_cap = (uint32_t)total_points;                 // worst case: every visible splat of every rank lands in one band
+    s.local_cap = local_points ? local_points : 1;
+    const uint32_t tx = (width + TILE - 1) / TILE, ty = (height + TILE - 1) / TILE;
+    for (uint32_t d = 0; d <= world; d++) s.band_y0[d] = (uint32_t)(((uint64_t)ty * d) / world);   // contiguous tile-row bands
+    // the pipeline buffers peers write into are allocated once and never move (IPC handles point at them)
+    ws_status st = ensure_capacity(r, s.recv_cap, tx * ty);
+    if (st != WS_OK) return st;
+    const size_t nl = s.local_cap, parts = (nl + 255) / 256;
+    CU(cudaMalloc(&s.l_splats, nl * 20)); CU(cudaMalloc(&s.l_keys, nl * 4)); CU(cudaMalloc(&s.l_vals, nl * 4)); CU(cudaMalloc(&s.l_rects, nl * 8));
+    s.route_words = parts * world * 2 + 4 * 256 + 16;
+    CU(cudaMalloc(&s.d_route, s.route_words * 4));
+    s.part_band_counts = s.d_route; s.part_band_bases = s.d_route + parts * world; s.hist_dummy = s.d_route + parts * world * 2;
+    s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_3x64)
+{
+    if (!r || !handles_3x64) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (r->shard.world < 1 || !r->d_splats) return fail(WS_ERR_INVALID_ARGUMENT, "call ws_renderer_shard_configure first");
+    CU(cudaSetDevice(r->ctx->device));
+    cudaIpcMemHandle_t h[3];
+    CU(cudaIpcGetMemHandle(&h[0], r->d_splats)); CU(cudaIpcGetMemHandle(&h[1], r->d_keys[0])); CU(cudaIpcGetMemHandle(&h[2], r->d_rects));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles_3x64, h, sizeof h);
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_handles)
+{
+    if (!r || !all_handles) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    ShardState &s = r->shard;
+    if (s.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "call ws_renderer_shard_configure first");
+    CU(cudaSetDevice(r->ctx->device));
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (uint32_t p = 0; p < s.world; p++) {
+        if (p == s.rank || s.opened[p]) continue;
+        void *a = nullptr, *b = nullptr, *c = nullptr;
+        CU(cudaIpcOpenMemHandle(&a, h[p * 3 + 0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&b, h[p * 3 + 1], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c, h[p * 3 + 2], cudaIpcMemLazyEnablePeerAccess));
+        s.peer_splats[p] = static_cast<uint32_t *>(a); s.peer_keys[p] = static_cast<uint32_t *>(b); s.peer_rects[p] = static_cast<uint2 *>(c);
+        s.opened[p] = true;
+    }
+    s.imported = true;
+    return WS_OK;
+}
+
+static void fill_route_args(ws_renderer *r, RouteArgs &a)
+{
+    ShardState &s = r->shard;
+    a.l_splats = s.l_splats; a.l_keys = s.l_keys; a.l_rects = s.l_rects; a.counters = r->d_counters;
+    a.world = s.world; a.rank = s.rank;
+    for (int d = 0; d < 9; d++) a.band_y0[d] = s.band_y0[d < (int)s.world + 1 ? d : s.world];
+    a.part_band_counts = s.part_band_counts; a.part_band_bases = s.part_band_bases;
+    a.totals = nullptr; a.matrix = nullptr;
+    for (int p = 0; p < 8; p++) { a.peer_splats[p] = s.peer_splats[p]; a.peer_keys[p] = s.peer_keys[p]; a.peer_rects[p] = s.peer_rects[p]; }
+    a.recv_cap = s.recv_cap; a.err = &r->d_counters->error_flags;
+}
+
+extern "C" ws_status ws_renderer_shard_begin(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
+                                             uint32_t *totals_row_device, void *cuda_stream)
+{
+    ws_status st = validate_frame(r, pc, args);
+    if (st != WS_OK) return st;
+    ShardState &s = r->shard;
+    if (s.world < 1 || !totals_row_device) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding / NULL totals");
+    if (s.world > 1 && !s.imported) return fail(WS_ERR_INVALID_ARGUMENT, "peer handles not imported");
+    if (args->viewport[0] != s.width || args->viewport[1] != s.height) return fail(WS_ERR_INVALID_ARGUMENT, "viewport differs from ws_renderer_shard_configure");
+    if (pc->n > s.local_cap) return fail(WS_ERR_INVALID_ARGUMENT, "local shard larger than configured");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    st = begin_frame(r, pc, args, s.recv_cap, stream);
+    if (st != WS_OK) return st;
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
+    {   // ---- stage 1 on the local shard, into the local staging arrays
+        PreprocessArgs a;
+        a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
+        a.uniforms = r->d_uniforms;
+        a.splats = s.l_splats; a.depth_keys = s.l_keys; a.slot_vals = s.l_vals; a.rects = s.l_rects;
+        a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
+        a.hist = s.hist_dummy; a.counters = r->d_counters;      // the consumer histograms the keys it RECEIVES
+        CU(cudaMemsetAsync(s.hist_dummy, 0, 4 * 256 * 4, stream));
+        CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
+    }
+    {   // ---- routing pass 1+2: how many local splats go to each band
+        RouteArgs a; fill_route_args(r, a);
+        a.totals = totals_row_device;
+        CU(launch_route_count(a, r->ctx->sm_count * 8, stream));
+    }
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
+    r->last_stream = stream; r->last_n = pc->n;
+    s.phase = 1;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_shard_exchange(ws_renderer *r, const uint32_t *matrix_device, void *cuda_stream)
+{
+    if (!r || !matrix_device) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    ShardState &s = r->shard;
+    if (s.phase != 1) return fail(WS_ERR_NOT_PREPARED, "ws_renderer_shard_begin must precede exchange");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    RouteArgs a; fill_route_args(r, a);
+    a.matrix = matrix_device;
+    CU(launch_route_scatter(a, r->ctx->sm_count * 8, stream));      // stores straight into the owners' buffers (NVLink)
+    s.phase = 2;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_shard_finish(ws_renderer *r, const uint32_t *matrix_device, void *cuda_stream)
+{
+    if (!r || !matrix_device) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    ShardState &s = r->shard;
+    if (s.phase != 2) return fail(WS_ERR_NOT_PREPARED, "ws_renderer_shard_exchange (and the cross-rank barrier) must precede finish");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    CU(launch_shard_finish(matrix_device, s.world, s.rank, s.recv_cap, r->d_counters, r->d_vals[0], r->ctx->sm_count * 4, stream));
+    CU(launch_sort_histogram(r->d_keys[0], &r->d_counters->num_visible, r->n_cap, r->d_hist_depth, r->depth_passes, r->ctx->sm_count * 4, stream));
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));     // "preprocess" = stage 1 + exchange in sharded mode
+    ws_status st = enqueue_stage2(r, stream);
+    if (st != WS_OK) return st;
+    r->prepared = true;
+    r->last_stream = stream;
+    s.phase = 0;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_shard_band(const ws_renderer *r, uint32_t *first_row, uint32_t *num_rows)
+{
+    if (!r || !first_row || !num_rows) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    const ShardState &s = r->shard;
+    if (s.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
+    const uint32_t y0 = s.band_y0[s.rank] * TILE, y1 = s.band_y0[s.rank + 1] * TILE;
+    *first_row = y0 < s.height ? y0 : s.height;
+    *num_rows = (y1 < s.height ? y1 : s.height) - *first_row;
+    return WS_OK;
+}
+
 static size_t bytes_per_pixel(ws_format f) { return f == WS_FORMAT_RGBA8_UNORM ? 4 : (f == WS_FORMAT_RGBA16_FLOAT ? 8 : 16); }
+
+static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch, const double clear[4],
+                             void *cuda_stream, uint32_t tile_y0, uint32_t tile_rows);
 
 extern "C" ws_status ws_renderer_render(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch,
                                         const double clear[4], void *cuda_stream)
+{
+    if (r && r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "sharded renderer: use ws_renderer_render_band");
+    return render_rows(r, pc, dst, row_pitch, clear, cuda_stream, 0, r ? r->h_uniforms.tiles_y : 0);
+}
+
+// the rows of this rank's band only; dst row 0 = first pixel row of the band (ws_renderer_shard_band)
+extern "C" ws_status ws_renderer_render_band(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch,
+                                             const double clear[4], void *cuda_stream)
+{
+    if (!r || r->shard.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
+    const ShardState &s = r->shard;
+    return render_rows(r, pc, dst, row_pitch, clear, cuda_stream, s.band_y0[s.rank], s.band_y0[s.rank + 1] - s.band_y0[s.rank]);
+}
+
+static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch, const double clear[4],
+                             void *cuda_stream, uint32_t tile_y0, uint32_t tile_rows)
 {
     if (!r || !pc || !dst) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!r->prepared) return fail(WS_ERR_NOT_PREPARED, "prepare() must precede render()");
@@ -588,9 +812,10 @@ extern "C" ws_status ws_renderer_render(ws_renderer *r, ws_pointcloud *pc, void 
     CompositeArgs a;
     a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
     a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
+    a.tile_y0 = tile_y0;
     for (int i = 0; i < 4; i++) a.clear[i] = clear ? (float)clear[i] : 0.f;
     if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND0], stream));
-    CU(launch_composite(a, U.tiles_x, U.tiles_y, stream));
+    if (tile_rows) CU(launch_composite(a, U.tiles_x, tile_rows, stream));
     if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND1], stream));
     r->rendered = true;
     r->last_stream = stream;

@@ -46,7 +46,7 @@ composite_kernel(CompositeArgs a)
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = a.uniforms->width, H = a.uniforms->height;
-    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y + a.tile_y0;
     const uint32_t tile = tile_y * gridDim.x + tile_x;
     uint2 range = a.ranges[tile];
     range.y = ~range.y;                                  // stored complemented (atomicMin in the sort's last pass)
@@ -139,7 +139,7 @@ composite_kernel(CompositeArgs a)
     if (inside) {
         const float r = cr + a.clear[0] * T, g = cg + a.clear[1] * T, b = cb + a.clear[2] * T;
         const float al = (1.f - T) + a.clear[3] * T;
-        uint8_t *row = reinterpret_cast<uint8_t *>(a.dst) + (size_t)py * a.row_pitch;
+        uint8_t *row = reinterpret_cast<uint8_t *>(a.dst) + (size_t)(py - a.tile_y0 * TILE) * a.row_pitch;
         if (FORMAT == 2) {
             reinterpret_cast<float4 *>(row)[px] = make_float4(r, g, b, al);
         } else if (FORMAT == 1) {

@@ -1,0 +1,193 @@
+// shard.cu -- multi-GPU exchange step of the splat render path.
+//
+// The reference is single-GPU.  The sharded path splits one frame over G GPUs of a box:
+//   stage 1              by Gaussian index: rank r preprocesses Gaussians [r*N/G, (r+1)*N/G);
+//   stages 2 and 3       by tile-row band: rank d depth-sorts, bins and composites only the
+//                        splats that touch its band of 16-pixel tile rows.
+// Alpha compositing is order dependent over ALL splats of a pixel, so partial images cannot be
+// merged (no sort-last); what is exchanged between the two phases are the visible splats
+// themselves: 32 B each (20-B Splat, 4-B depth key, 8-B tile rectangle clipped to the band).
+//
+// The exchange is one kernel that STORES DIRECTLY INTO THE DESTINATION GPU'S BUFFERS through
+// peer-mapped pointers (cudaIpc handles, NVLink 5 / NVSwitch): routing (which band), compaction
+// (ballot ranks + scanned per-partition bases) and the transfer are fused; no send staging, no
+// NCCL all-to-all with host-known sizes.  Destination offsets come from a G x G matrix of counts
+// that the ranks all-gather (G*4 B each, NCCL) between the count pass and the scatter pass.
+// Records arrive ordered by (source rank, source slot) = global Gaussian index order, so the
+// stable depth sort that follows breaks ties exactly like the single-GPU path and the G-GPU
+// frame is bit-identical to the 1-GPU frame.
+#include "ws_device.cuh"
+#include "ws_kernels.h"
+
+namespace ws {
+
+namespace {
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_WARPS = RT_THREADS / 32;
+
+__device__ __forceinline__ bool touches_band(uint2 rect, uint32_t b0, uint32_t b1)
+{
+    const uint32_t y0 = rect.x >> 16, h = rect.y >> 16, w = rect.y & 0xffffu;
+    return (w != 0u) && (h != 0u) && (y0 < b1) && (y0 + h > b0);
+}
+
+// ---- pass 1: per 256-slot partition, how many local splats go to each band
+__global__ void __launch_bounds__(RT_THREADS)
+route_count_kernel(RouteArgs a)
+{
+    const unsigned tid = threadIdx.x;
+    const uint32_t V = a.counters->num_visible;
+    const uint32_t nparts = (V + RT_THREADS - 1u) / RT_THREADS;
+    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
+        const uint32_t slot = part * RT_THREADS + tid;
+        const uint2 rc = (slot < V) ? a.l_rects[slot] : make_uint2(0u, 0u);
+        for (uint32_t d = 0; d < a.world; d++) {
+            const uint32_t c = (uint32_t)__syncthreads_count(touches_band(rc, a.band_y0[d], a.band_y0[d + 1]) ? 1 : 0);
+            if (tid == 0) a.part_band_counts[(size_t)part * a.world + d] = c;
+        }
+    }
+}
+
+// ---- pass 2 (one CTA): per band, exclusive scan over the partitions; totals = this rank's matrix row
+__global__ void __launch_bounds__(1024)
+route_scan_kernel(RouteArgs a)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_total;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t V = a.counters->num_visible;
+    const uint32_t nparts = (V + RT_THREADS - 1u) / RT_THREADS;
+    const uint32_t per = (nparts + 1023u) / 1024u;
+    const uint32_t lo = tid * per, hi = (lo + per < nparts) ? lo + per : nparts;
+    for (uint32_t d = 0; d < a.world; d++) {
+        uint32_t sum = 0;
+        for (uint32_t i = lo; i < hi; i++) sum += a.part_band_counts[(size_t)i * a.world + d];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = s_w[lane];
+            uint32_t vi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+                if ((int)lane >= o) vi += t;
+            }
+            s_w[lane] = vi - v;
+            if (lane == 31) s_total = vi;
+        }
+        __syncthreads();
+        uint32_t run = s_w[warp] + incl - sum;
+        for (uint32_t i = lo; i < hi; i++) {
+            const uint32_t c = a.part_band_counts[(size_t)i * a.world + d];
+            a.part_band_bases[(size_t)i * a.world + d] = run;
+            run += c;
+        }
+        if (tid == 0) a.totals[d] = (nparts > 0u) ? s_total : 0u;
+        __syncthreads();
+    }
+}
+
+// ---- pass 3: routing + compaction + transfer, fused: store records into the owners' buffers
+__global__ void __launch_bounds__(RT_THREADS)
+route_scatter_kernel(RouteArgs a)
+{
+    __shared__ uint32_t s_list[RT_THREADS];      // local slots bound for the current band, in slot order
+    __shared__ uint32_t s_wcnt[RT_WARPS];
+    __shared__ uint32_t s_recv_off[8];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t V = a.counters->num_visible;
+    const uint32_t nparts = (V + RT_THREADS - 1u) / RT_THREADS;
+    if (tid < a.world) {                          // where this rank's records start in each destination
+        uint32_t off = 0;
+        for (uint32_t s = 0; s < a.rank; s++) off += a.matrix[s * a.world + tid];
+        s_recv_off[tid] = off;
+    }
+    __syncthreads();
+    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
+        const uint32_t slot = part * RT_THREADS + tid;
+        const uint2 rc = (slot < V) ? a.l_rects[slot] : make_uint2(0u, 0u);
+        for (uint32_t d = 0; d < a.world; d++) {
+            const uint32_t b0 = a.band_y0[d], b1 = a.band_y0[d + 1];
+            const bool go = touches_band(rc, b0, b1);
+            const unsigned bal = __ballot_sync(0xffffffffu, go);
+            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t woff = 0, cnt = 0;
+#pragma unroll
+            for (int w = 0; w < RT_WARPS; w++) { const uint32_t c = s_wcnt[w]; if (w < (int)warp) woff += c; cnt += c; }
+            if (go) s_list[woff + __popc(bal & lanemask_lt())] = slot;
+            __syncthreads();
+            const uint32_t dst0 = s_recv_off[d] + a.part_band_bases[(size_t)part * a.world + d];
+            if (dst0 + cnt > a.recv_cap) {
+                if (tid == 0 && cnt) atomicOr(a.err, 2u);                       // receiver capacity exceeded: nothing is written
+            } else {
+                uint32_t *ds = a.peer_splats[d];
+                for (uint32_t i = tid; i < cnt * 5u; i += RT_THREADS) {
+                    const uint32_t e = i / 5u, k = i - e * 5u;
+                    ds[(size_t)(dst0 + e) * 5u + k] = a.l_splats[(size_t)s_list[e] * 5u + k];
+                }
+                if (tid < cnt) {
+                    const uint32_t src = s_list[tid];
+                    a.peer_keys[d][dst0 + tid] = a.l_keys[src];
+                    const uint2 r = a.l_rects[src];                            // clip the rectangle to the band's tile rows
+                    const uint32_t y0 = r.x >> 16, h = r.y >> 16;
+                    const uint32_t ny0 = y0 > b0 ? y0 : b0;
+                    const uint32_t ny1 = (y0 + h < b1) ? y0 + h : b1;
+                    a.peer_rects[d][dst0 + tid] = make_uint2((r.x & 0xffffu) | (ny0 << 16), (r.y & 0xffffu) | ((ny1 - ny0) << 16));
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- after the exchange: V' = records received; payload iota for the depth sort
+__global__ void __launch_bounds__(256)
+shard_finish_kernel(const uint32_t *matrix, uint32_t world, uint32_t rank, uint32_t recv_cap,
+                    FrameCounters *counters, uint32_t *vals)
+{
+    uint32_t v = 0;
+    for (uint32_t s = 0; s < world; s++) v += matrix[s * world + rank];
+    if (v > recv_cap) v = recv_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters->num_local_visible = counters->num_visible; }
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < v; i += gridDim.x * 256u) vals[i] = i;
+}
+__global__ void shard_set_visible_kernel(const uint32_t *matrix, uint32_t world, uint32_t rank, uint32_t recv_cap, FrameCounters *counters)
+{
+    uint32_t v = 0;
+    for (uint32_t s = 0; s < world; s++) v += matrix[s * world + rank];
+    if (v > recv_cap) { v = recv_cap; atomicOr(&counters->error_flags, 2u); }
+    counters->num_visible = v;
+}
+
+}  // namespace
+
+cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream)
+{
+    route_count_kernel<<<grid, RT_THREADS, 0, stream>>>(a);
+    route_scan_kernel<<<1, 1024, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_route_scatter(const RouteArgs &a, int grid, cudaStream_t stream)
+{
+    route_scatter_kernel<<<grid, RT_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_finish(const uint32_t *matrix, uint32_t world, uint32_t rank, uint32_t recv_cap,
+                                FrameCounters *counters, uint32_t *vals, int grid, cudaStream_t stream)
+{
+    shard_finish_kernel<<<grid, 256, 0, stream>>>(matrix, world, rank, recv_cap, counters, vals);
+    shard_set_visible_kernel<<<1, 1, 0, stream>>>(matrix, world, rank, recv_cap, counters);
+    return cudaGetLastError();
+}
+
+}  // namespace ws

@@ -44,7 +44,9 @@ struct FrameCounters {
     uint32_t num_pairs;         // P (pairs needed, may exceed capacity)
     uint32_t pair_overflow;     // 1 if P > capacity
     uint32_t error_flags;       // bit 0: a look-back spin exceeded SPIN_LIMIT (never expected)
-    uint32_t ticket[12];        // dynamic partition tickets: [0] preprocess, [1] binning, [2..] sort passes
+    uint32_t ticket[12];        // dynamic partition tickets: [2..5] depth passes, [6..8] tile passes
+    uint32_t num_local_visible; // sharded mode: survivors of the local shard (num_visible then counts the received ones)
+    uint32_t _r1[3];
 };
 
 constexpr int TILE = 16;                    // 16x16 pixel tiles

@@ -77,7 +77,26 @@ struct CompositeArgs {
     uint32_t row_pitch;           // bytes
     int format;                   // ws_format
     float clear[4];
+    uint32_t tile_y0;             // first tile row to composite (sharded rendering: this rank's band); dst row 0 = that row
 };
 cudaError_t launch_composite(const CompositeArgs &a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream);
+
+// ---- multi-GPU exchange (shard.cu) ---------------------------------------------------------------
+struct RouteArgs {
+    const uint32_t *l_splats, *l_keys; const uint2 *l_rects;   // stage-1 output of the local shard (slot order)
+    const FrameCounters *counters;                             // num_visible = local V
+    uint32_t world, rank;
+    uint32_t band_y0[9];                                       // rank d owns tile rows [band_y0[d], band_y0[d+1])
+    uint32_t *part_band_counts, *part_band_bases;              // [ceil(V/256)][world]
+    uint32_t *totals;                                          // out (pass 2): this rank's row of the G x G count matrix
+    const uint32_t *matrix;                                    // in (pass 3): the all-gathered matrix [src][dst]
+    uint32_t *peer_splats[8], *peer_keys[8]; uint2 *peer_rects[8];   // destination buffers (peer-mapped for other ranks)
+    uint32_t recv_cap;
+    uint32_t *err;
+};
+cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream);
+cudaError_t launch_route_scatter(const RouteArgs &a, int grid, cudaStream_t stream);
+cudaError_t launch_shard_finish(const uint32_t *matrix, uint32_t world, uint32_t rank, uint32_t recv_cap,
+                                FrameCounters *counters, uint32_t *vals, int grid, cudaStream_t stream);
 
 }  // namespace ws

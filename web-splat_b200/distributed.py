@@ -1,0 +1,116 @@
+"""Sharded rendering of ONE frame over the GPUs of a box.
+
+Host layer of csrc/shard.cu: one process per GPU (torchrun), torch.distributed (NCCL over
+NVLink 5 / NVSwitch) for the plumbing -- the G x G count matrix, the barrier after the peer-memory
+exchange and the gather of the finished bands -- while the splats themselves move by direct stores
+into the owners' buffers from inside the exchange kernel.  The reference is single-GPU; nothing here
+has an upstream counterpart beyond GaussianRenderer::prepare/render (renderer.rs:191-260).
+"""
+import ctypes as C
+
+import numpy as np
+
+
+def tile_row_bands(height, world):
+    """rank d owns tile rows [b[d], b[d+1]) of the ceil(height/16) rows -- mirrors ws_renderer_shard_configure."""
+    ty = (height + 15) // 16
+    return [(ty * d) // world for d in range(world + 1)]
+
+
+def shard_cloud(cloud, rank, world):
+    """Gaussians [rank*N/world, (rank+1)*N/world) of a cloud dict, keeping the GLOBAL bbox / centre
+    (clip box, scene centre and extent come from them: renderer.rs:622-651)."""
+    n = int(cloud["num_points"])
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    out = dict(cloud)
+    out["gaussians"] = cloud["gaussians"][lo:hi]
+    if cloud["compressed"]:
+        out["sh_coefs"] = cloud["sh_coefs"]              # codebooks are replicated
+    else:
+        out["sh_coefs"] = cloud["sh_coefs"][lo:hi]
+    out["num_points"] = hi - lo
+    out["first_index"] = lo
+    return out
+
+
+def exchange_offsets(matrix, rank):
+    """Where rank `rank`'s records start in each destination (host mirror of route_scatter_kernel)."""
+    m = np.asarray(matrix)
+    return m[:rank].sum(axis=0)
+
+
+class ShardedRenderer:
+    """GaussianRenderer over `world` GPUs.  Every rank calls frame() with the same SplattingArgs;
+    the full frame is returned on every rank (device tensor) after the band all-gather."""
+
+    def __init__(self, ws, ctx, color_format, sh_deg, compressed, pc, total_points, viewport, group=None,
+                 pair_capacity=None):
+        import torch
+        import torch.distributed as dist
+        self.ws, self.torch, self.dist = ws, torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.pc = pc
+        self.W, self.H = int(viewport[0]), int(viewport[1])
+        self.format = int(color_format)
+        self.r = ws.GaussianRenderer.new(ctx, color_format, sh_deg, compressed)
+        if pair_capacity:
+            self.r.set_pair_capacity(pair_capacity)
+        L = ws.lib()
+        ws._check(L.ws_renderer_shard_configure(self.r._h, self.rank, self.world, int(total_points), pc.num_points(), self.W, self.H))
+        self.r._viewport = (self.W, self.H)
+        handles = torch.zeros(192, dtype=torch.uint8)
+        ws._check(L.ws_renderer_shard_export(self.r._h, C.c_void_p(handles.data_ptr())))
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            allh = [torch.zeros(192, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            dist.all_gather(allh, handles.to(dev), group=group)
+            allh = torch.cat([h.cpu() for h in allh]).contiguous()
+            ws._check(L.ws_renderer_shard_import(self.r._h, C.c_void_p(allh.data_ptr())))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.row = torch.zeros(self.world, dtype=torch.int32, device=dev)
+        self.matrix = torch.zeros(self.world * self.world, dtype=torch.int32, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        first, rows = C.c_uint32(), C.c_uint32()
+        ws._check(L.ws_renderer_shard_band(self.r._h, C.byref(first), C.byref(rows)))
+        self.first_row, self.num_rows = first.value, rows.value
+        self.bands = tile_row_bands(self.H, self.world)
+        self.max_rows = max(min(self.bands[d + 1] * 16, self.H) - min(self.bands[d] * 16, self.H) for d in range(self.world))
+        dt = {0: torch.uint8, 1: torch.float16, 2: torch.float32}[self.format]
+        self.band = torch.zeros((self.max_rows, self.W, 4), dtype=dt, device=dev)
+        self.gathered = torch.zeros((self.world, self.max_rows, self.W, 4), dtype=dt, device=dev)
+        self.frame_out = torch.zeros((self.H, self.W, 4), dtype=dt, device=dev)
+
+    def frame(self, args, clear=(0.0, 0.0, 0.0, 0.0), gather=True):
+        """Enqueue one frame on torch's current stream; returns the assembled frame (device tensor)."""
+        torch, dist, ws = self.torch, self.dist, self.ws
+        L = ws.lib()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        a = args._c()
+        ws._check(L.ws_renderer_shard_begin(self.r._h, self.pc._h, C.byref(a), C.c_void_p(self.row.data_ptr()), stream))
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.matrix, self.row, group=self.group)            # G x G counts
+        else:
+            self.matrix.copy_(self.row)
+        ws._check(L.ws_renderer_shard_exchange(self.r._h, C.c_void_p(self.matrix.data_ptr()), stream))
+        if self.world > 1:
+            dist.all_reduce(self.flag, group=self.group)                                       # every rank's stores have landed
+        ws._check(L.ws_renderer_shard_finish(self.r._h, C.c_void_p(self.matrix.data_ptr()), stream))
+        clr = (C.c_double * 4)(*[float(c) for c in clear])
+        pitch = self.W * ws._BPP[self.format]
+        ws._check(L.ws_renderer_render_band(self.r._h, self.pc._h, C.c_void_p(self.band.data_ptr()), pitch, C.byref(clr), stream))
+        if not gather:
+            return self.band[: self.num_rows]
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.band, group=self.group)
+            for d in range(self.world):
+                y0, y1 = min(self.bands[d] * 16, self.H), min(self.bands[d + 1] * 16, self.H)
+                if y1 > y0:
+                    self.frame_out[y0:y1].copy_(self.gathered[d, : y1 - y0])
+        else:
+            self.frame_out.copy_(self.band[: self.H])
+        return self.frame_out
+
+    def stats(self, allow_overflow=False):
+        return self.r.stats(allow_overflow)
