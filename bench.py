@@ -191,6 +191,10 @@ def run_ours(args):
     if world > 1:
         import bench_multi          # multi-GPU path lives next to this file
         return bench_multi.run(args)
+    if args.gpus > 1:               # launched without torchrun: start one process per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)

@@ -1,0 +1,144 @@
+"""Multi-GPU arm of bench.py (imported when WORLD_SIZE > 1): strong scaling of the SAME frame
+(cfg3 by default) over N GPUs of one box, one process per GPU (torchrun), NCCL for the plumbing,
+splats exchanged by direct peer-memory stores (web-splat_b200/csrc/shard.cu)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def run(args):
+    import torch
+    import torch.distributed as dist
+    import bench
+    import websplat_b200 as ws
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout; the contract is ONE JSON
+    # line there, so stdout is parked on stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # one process generates the cloud, the others load it (identical bytes on every rank)
+    if local == 0:
+        cloud, W, H, views = bench.make_workload(args.workload)
+    dist.barrier()
+    if local != 0:
+        cloud, W, H, views = bench.make_workload(args.workload)
+    ctx = ws.Context(local)
+    shard = ws.shard_cloud(cloud, rank, world)
+    gen = ws.GenericGaussianPointCloud(shard["gaussians"], shard["sh_coefs"], shard["sh_deg"], shard["num_points"],
+                                       ws.Aabb(cloud["aabb_min"], cloud["aabb_max"]), cloud["center"],
+                                       compressed=cloud["compressed"], covars=cloud.get("covars"), quantization=cloud.get("quantization"))
+    pc = ws.PointCloud.new(ctx, gen)
+    fmt = ws.FORMAT_RGBA16_FLOAT
+    N = int(cloud["num_points"])
+    sh = ws.ShardedRenderer(ws, ctx, fmt, cloud["sh_deg"], cloud["compressed"], pc, N, (W, H),
+                            pair_capacity=min(max(8 * N // world + (1 << 22), 1 << 22), (1 << 30) - 1))
+    fargs = [bench.frame_args(ws, cloud, v, W, H) for v in views]
+    K, Wu = args.steps, max(args.warmup, 3)
+    host = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2)] if rank == 0 else None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only: frame assembled on every rank's device, no host copy ------------------------
+    sh.r.set_timing(False)
+    for i in range(Wu):
+        sh.frame(fargs[i % len(fargs)])
+    sync_all()
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        sh.frame(fargs[(Wu + i) % len(fargs)])
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.finish() if sampler else None
+
+    # ---- e2e: rank 0 additionally downloads every frame into pinned host memory -------------------
+    for i in range(Wu):
+        f = sh.frame(fargs[i % len(fargs)])
+        if rank == 0:
+            host[i & 1].copy_(f, non_blocking=True)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(K):
+        f = sh.frame(fargs[(Wu + i) % len(fargs)])
+        if rank == 0:
+            host[i & 1].copy_(f, non_blocking=True)
+    sync_all()
+    e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e.item())
+
+    # ---- per-stage breakdown (max over ranks of each stage) ----------------------------------------
+    sh.r.set_timing(True)
+    keys = ("ms_preprocess", "ms_sort", "ms_blend", "ms_depth_sort", "ms_binning", "ms_tile_sort")
+    acc = np.zeros(len(keys)); vv = []; pp = []
+    for i in range(min(K, 36)):
+        sh.frame(fargs[(Wu + i) % len(fargs)])
+        torch.cuda.synchronize()
+        s = sh.stats()
+        acc += [s[k] for k in keys]; vv.append(s["num_visible"]); pp.append(s["num_pairs"])
+    acc /= min(K, 36)
+    t = torch.tensor(list(acc) + [float(np.mean(vv)), float(np.mean(pp))], device="cuda", dtype=torch.float64)
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    # ---- phase timeline of the sharded frame (events between the phases, rank 0's view) ------------
+    phases = {}
+    for i in range(12):
+        marks = []
+        sh.frame(fargs[(Wu + i) % len(fargs)], marks=marks)
+        torch.cuda.synchronize()
+        for (la, ea), (lb, eb) in zip(marks[:-1], marks[1:]):
+            phases[lb] = phases.get(lb, 0.0) + ea.elapsed_time(eb) / 12.0
+    if rank == 0:
+        peak, peak_src, _ = bench.measured_peaks()
+        fps = K / (ms_total * 1e-3)
+        stage = {k[3:]: float(tmax[i]) for i, k in enumerate(keys)}
+        V_sum, P_sum = float(tsum[-2]), float(tsum[-1])
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        bytes_sort_blend = 4 * V_sum * 16 + V_sum * 12 + P_sum * 8 + 2 * P_sum * 16 + P_sum * 24 + W * H * 8
+        sb_ms = stage["sort"] + stage["blend"]
+        line = {
+            "metric": bench.METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wu,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": bench.workload_name(args.workload, cloud, W, H), "target_format": "rgba16float",
+                       "parallelism": "stage 1 sharded by Gaussian index, stages 2-3 by tile-row band, peer-memory exchange",
+                       "l2": "inputs larger than L2; no flush needed", "N": N, "V_received_sum": V_sum, "P_sum": P_sum, "tiles": T},
+            "ms_per_frame": {"preprocess+exchange": stage["preprocess"], "sort": stage["sort"], "blend": stage["blend"],
+                             "depth_sort": stage["depth_sort"], "binning": stage["binning"], "tile_sort": stage["tile_sort"],
+                             "note": "max over ranks of each stage", "phases_rank0": phases},
+            "roofline": {"kernel": "sort+blend (all ranks)", "bound": "hbm", "achieved": bytes_sort_blend / (sb_ms * 1e-3) / 1e9 if sb_ms > 0 else 0.0,
+                         "peak": peak * world, "unit": "GB/s", "frac": (bytes_sort_blend / (sb_ms * 1e-3) / 1e9) / (peak * world) if sb_ms > 0 else 0.0,
+                         "traffic": None, "peak_source": peak_src + " x n_gpus"},
+            "cpu_baseline": None,
+            "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 448 * world, "d2h_bytes_per_step": W * H * 8},
+            "gpu_launches": K * world * 19,
+            "clocks": clocks,
+        }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

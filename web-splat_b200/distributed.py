@@ -82,34 +82,51 @@ class ShardedRenderer:
         self.gathered = torch.zeros((self.world, self.max_rows, self.W, 4), dtype=dt, device=dev)
         self.frame_out = torch.zeros((self.H, self.W, 4), dtype=dt, device=dev)
 
-    def frame(self, args, clear=(0.0, 0.0, 0.0, 0.0), gather=True):
-        """Enqueue one frame on torch's current stream; returns the assembled frame (device tensor)."""
+    def frame(self, args, clear=(0.0, 0.0, 0.0, 0.0), gather=True, marks=None):
+        """Enqueue one frame on torch's current stream; returns the assembled frame (device tensor).
+        `marks` (optional list) receives (label, torch.cuda.Event) pairs between the phases."""
         torch, dist, ws = self.torch, self.dist, self.ws
         L = ws.lib()
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def mark(label):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((label, e))
+
         a = args._c()
+        mark("start")
         ws._check(L.ws_renderer_shard_begin(self.r._h, self.pc._h, C.byref(a), C.c_void_p(self.row.data_ptr()), stream))
+        mark("stage1+route_count")
         if self.world > 1:
             dist.all_gather_into_tensor(self.matrix, self.row, group=self.group)            # G x G counts
         else:
             self.matrix.copy_(self.row)
+        mark("allgather_counts")
         ws._check(L.ws_renderer_shard_exchange(self.r._h, C.c_void_p(self.matrix.data_ptr()), stream))
+        mark("exchange_kernel")
         if self.world > 1:
             dist.all_reduce(self.flag, group=self.group)                                       # every rank's stores have landed
+        mark("barrier")
         ws._check(L.ws_renderer_shard_finish(self.r._h, C.c_void_p(self.matrix.data_ptr()), stream))
+        mark("sort+binning")
         clr = (C.c_double * 4)(*[float(c) for c in clear])
         pitch = self.W * ws._BPP[self.format]
         ws._check(L.ws_renderer_render_band(self.r._h, self.pc._h, C.c_void_p(self.band.data_ptr()), pitch, C.byref(clr), stream))
+        mark("composite_band")
         if not gather:
             return self.band[: self.num_rows]
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered, self.band, group=self.group)
+            mark("allgather_bands")
             for d in range(self.world):
                 y0, y1 = min(self.bands[d] * 16, self.H), min(self.bands[d + 1] * 16, self.H)
                 if y1 > y0:
                     self.frame_out[y0:y1].copy_(self.gathered[d, : y1 - y0])
         else:
             self.frame_out.copy_(self.band[: self.H])
+        mark("assemble")
         return self.frame_out
 
     def stats(self, allow_overflow=False):
