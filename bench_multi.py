@@ -55,8 +55,9 @@ def run(args):
 
     # ---- kernel-only: frame assembled on every rank's device, no host copy ------------------------
     sh.r.set_timing(False)
+    # the bands are stored straight into rank 0's assembled frame (peer memory) by the compositor
     for i in range(Wu):
-        sh.frame(fargs[i % len(fargs)])
+        sh.frame_to_root(fargs[i % len(fargs)])
     sync_all()
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -64,7 +65,7 @@ def run(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        sh.frame(fargs[(Wu + i) % len(fargs)])
+        sh.frame_to_root(fargs[(Wu + i) % len(fargs)])
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -74,15 +75,11 @@ def run(args):
 
     # ---- e2e: rank 0 additionally downloads every frame into pinned host memory -------------------
     for i in range(Wu):
-        f = sh.frame(fargs[i % len(fargs)])
-        if rank == 0:
-            host[i & 1].copy_(f, non_blocking=True)
+        sh.frame_to_root(fargs[i % len(fargs)], host=host[i & 1] if rank == 0 else None)
     sync_all()
     t0 = time.perf_counter()
     for i in range(K):
-        f = sh.frame(fargs[(Wu + i) % len(fargs)])
-        if rank == 0:
-            host[i & 1].copy_(f, non_blocking=True)
+        sh.frame_to_root(fargs[(Wu + i) % len(fargs)], host=host[i & 1] if rank == 0 else None)
     sync_all()
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
@@ -93,7 +90,7 @@ def run(args):
     keys = ("ms_preprocess", "ms_sort", "ms_blend", "ms_depth_sort", "ms_binning", "ms_tile_sort")
     acc = np.zeros(len(keys)); vv = []; pp = []
     for i in range(min(K, 36)):
-        sh.frame(fargs[(Wu + i) % len(fargs)])
+        sh.frame_to_root(fargs[(Wu + i) % len(fargs)])
         torch.cuda.synchronize()
         s = sh.stats()
         acc += [s[k] for k in keys]; vv.append(s["num_visible"]); pp.append(s["num_pairs"])
@@ -105,7 +102,8 @@ def run(args):
     phases = {}
     for i in range(12):
         marks = []
-        sh.frame(fargs[(Wu + i) % len(fargs)], marks=marks)
+        dist.barrier()
+        sh.frame_to_root(fargs[(Wu + i) % len(fargs)], marks=marks)
         torch.cuda.synchronize()
         for (la, ea), (lb, eb) in zip(marks[:-1], marks[1:]):
             phases[lb] = phases.get(lb, 0.0) + ea.elapsed_time(eb) / 12.0
@@ -132,7 +130,7 @@ def run(args):
                          "traffic": None, "peak_source": peak_src + " x n_gpus"},
             "cpu_baseline": None,
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 448 * world, "d2h_bytes_per_step": W * H * 8},
-            "gpu_launches": K * world * 19,
+            "gpu_launches": K * world * 19,     # per rank and frame: 3 stage-1 + 3 routing + 3 finish/histogram + 6 onesweep + 3 binning + 1 composite
             "clocks": clocks,
         }
         sys.stdout.flush()

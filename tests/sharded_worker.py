@@ -41,6 +41,14 @@ def main():
                 same = torch.equal(ref, img)
                 ok = ok and same
                 print("n=%d %dx%d az=%.0f identical=%s V=%d" % (n, W, H, az, same, sh.stats()["num_visible"]), flush=True)
+            # the variant whose band gather is fused into the compositor (peer stores into rank 0's frame)
+            host = torch.zeros_like(img, device="cpu").pin_memory() if rank == 0 else None
+            sh.frame_to_root(args, clear=(0.1, 0.2, 0.3, 0.5), root=0, host=host)
+            torch.cuda.synchronize()
+            if rank == 0:
+                same2 = torch.equal(host, ref.cpu())
+                ok = ok and same2
+                print("   to_root identical=%s" % same2, flush=True)
             dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -32,6 +32,10 @@ def test_sharded_world1_equals_plain(ws, orc, ctx):
         img = sh.frame(args)
         torch.cuda.synchronize()
         assert torch.equal(img, t)
+    host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
+    sh.frame_to_root(args, host=host)
+    torch.cuda.synchronize()
+    assert torch.equal(host, t.cpu())
     st = sh.stats()
     # only splats that touch at least one tile are routed, so the received count can be below V
     assert st["num_visible"] <= plain.stats()["num_visible"] and st["num_pairs"] == plain.stats()["num_pairs"]

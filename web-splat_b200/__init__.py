@@ -123,6 +123,7 @@ EXPORTED_SYMBOLS = [
     "ws_renderer_camera_uniform", "ws_renderer_settings_uniform", "ws_version",
     "ws_renderer_shard_configure", "ws_renderer_shard_export", "ws_renderer_shard_import", "ws_renderer_shard_begin",
     "ws_renderer_shard_exchange", "ws_renderer_shard_finish", "ws_renderer_shard_band", "ws_renderer_render_band",
+    "ws_renderer_render_band_to_root", "ws_renderer_shard_frame", "ws_renderer_shard_download",
 ]
 
 _lib = None
@@ -190,6 +191,9 @@ def lib():
         "ws_renderer_shard_finish": (i32, [vp, vp, vp]),
         "ws_renderer_shard_band": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
         "ws_renderer_render_band": (i32, [vp, vp, vp, C.c_size_t, C.POINTER(C.c_double * 4), vp]),
+        "ws_renderer_render_band_to_root": (i32, [vp, vp, u32, C.POINTER(C.c_double * 4), vp]),
+        "ws_renderer_shard_frame": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "ws_renderer_shard_download": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

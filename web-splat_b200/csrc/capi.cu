@@ -290,6 +290,8 @@ struct ShardState {
     uint32_t *d_route = nullptr; size_t route_words = 0;
     uint32_t *part_band_counts = nullptr, *part_band_bases = nullptr, *hist_dummy = nullptr;
     uint32_t *peer_splats[8] = {}, *peer_keys[8] = {}; uint2 *peer_rects[8] = {};
+    uint8_t *peer_frame[8] = {};               // every rank's assembled-frame buffer (only the root's is written)
+    uint8_t *d_shard_frame = nullptr; size_t shard_frame_bytes = 0;
     bool opened[8] = {};
     bool imported = false;
     int phase = 0;
@@ -619,10 +621,11 @@ static void free_shard(ws_renderer *r)
     for (int p = 0; p < 8; p++) {
         if (s.opened[p]) {
             cudaIpcCloseMemHandle(s.peer_splats[p]); cudaIpcCloseMemHandle(s.peer_keys[p]); cudaIpcCloseMemHandle(s.peer_rects[p]);
+            cudaIpcCloseMemHandle(s.peer_frame[p]);
             s.opened[p] = false;
         }
     }
-    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route);
+    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame);
     s = ShardState();
 }
 
@@ -644,22 +647,26 @@ extern "C" ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, 
     // the pipeline buffers peers write into are allocated once and never move (IPC handles point at them)
     ws_status st = ensure_capacity(r, s.recv_cap, tx * ty);
     if (st != WS_OK) return st;
-    const size_t nl = s.local_cap, parts = (nl + 255) / 256;
+    const size_t nl = s.local_cap, parts = (nl + 1023) / 1024;          // routing partitions (shard.cu RT_PART)
     CU(cudaMalloc(&s.l_splats, nl * 20)); CU(cudaMalloc(&s.l_keys, nl * 4)); CU(cudaMalloc(&s.l_vals, nl * 4)); CU(cudaMalloc(&s.l_rects, nl * 8));
     s.route_words = parts * world * 2 + 4 * 256 + 16;
     CU(cudaMalloc(&s.d_route, s.route_words * 4));
     s.part_band_counts = s.d_route; s.part_band_bases = s.d_route + parts * world; s.hist_dummy = s.d_route + parts * world * 2;
-    s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects;
+    s.shard_frame_bytes = (size_t)width * height * (r->format == WS_FORMAT_RGBA8_UNORM ? 4 : (r->format == WS_FORMAT_RGBA16_FLOAT ? 8 : 16));
+    CU(cudaMalloc(&s.d_shard_frame, s.shard_frame_bytes));
+    s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects; s.peer_frame[rank] = s.d_shard_frame;
     return WS_OK;
 }
 
-extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_3x64)
+extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_4x64)
 {
+    void *handles_3x64 = handles_4x64;
     if (!r || !handles_3x64) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (r->shard.world < 1 || !r->d_splats) return fail(WS_ERR_INVALID_ARGUMENT, "call ws_renderer_shard_configure first");
     CU(cudaSetDevice(r->ctx->device));
-    cudaIpcMemHandle_t h[3];
+    cudaIpcMemHandle_t h[4];
     CU(cudaIpcGetMemHandle(&h[0], r->d_splats)); CU(cudaIpcGetMemHandle(&h[1], r->d_keys[0])); CU(cudaIpcGetMemHandle(&h[2], r->d_rects));
+    CU(cudaIpcGetMemHandle(&h[3], r->shard.d_shard_frame));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(handles_3x64, h, sizeof h);
     return WS_OK;
@@ -674,11 +681,13 @@ extern "C" ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_ha
     const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
     for (uint32_t p = 0; p < s.world; p++) {
         if (p == s.rank || s.opened[p]) continue;
-        void *a = nullptr, *b = nullptr, *c = nullptr;
-        CU(cudaIpcOpenMemHandle(&a, h[p * 3 + 0], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&b, h[p * 3 + 1], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&c, h[p * 3 + 2], cudaIpcMemLazyEnablePeerAccess));
+        void *a = nullptr, *b = nullptr, *c = nullptr, *f = nullptr;
+        CU(cudaIpcOpenMemHandle(&a, h[p * 4 + 0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&b, h[p * 4 + 1], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c, h[p * 4 + 2], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&f, h[p * 4 + 3], cudaIpcMemLazyEnablePeerAccess));
         s.peer_splats[p] = static_cast<uint32_t *>(a); s.peer_keys[p] = static_cast<uint32_t *>(b); s.peer_rects[p] = static_cast<uint2 *>(c);
+        s.peer_frame[p] = static_cast<uint8_t *>(f);
         s.opened[p] = true;
     }
     s.imported = true;
@@ -795,6 +804,33 @@ extern "C" ws_status ws_renderer_render_band(ws_renderer *r, ws_pointcloud *pc, 
     if (!r || r->shard.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
     const ShardState &s = r->shard;
     return render_rows(r, pc, dst, row_pitch, clear, cuda_stream, s.band_y0[s.rank], s.band_y0[s.rank + 1] - s.band_y0[s.rank]);
+}
+
+// stage 3 for this rank's band, stored straight into the ROOT rank's assembled frame through the
+// peer mapping (the gather of the bands is fused into the compositor's epilogue; the host layer only
+// adds a barrier).  ws_renderer_shard_frame / _download read the assembled frame on the root.
+extern "C" ws_status ws_renderer_render_band_to_root(ws_renderer *r, ws_pointcloud *pc, uint32_t root, const double clear[4], void *cuda_stream)
+{
+    if (!r || r->shard.world < 1 || root >= r->shard.world) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding / bad root");
+    const ShardState &s = r->shard;
+    if (!s.peer_frame[root]) return fail(WS_ERR_INVALID_ARGUMENT, "peer handles not imported");
+    const size_t pitch = s.shard_frame_bytes / s.height;
+    const uint32_t first = s.band_y0[s.rank] * TILE;
+    if (first >= s.height) { r->rendered = true; return WS_OK; }
+    return render_rows(r, pc, s.peer_frame[root] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], s.band_y0[s.rank + 1] - s.band_y0[s.rank]);
+}
+extern "C" ws_status ws_renderer_shard_frame(const ws_renderer *r, void **device_ptr, size_t *row_pitch_bytes)
+{
+    if (!r || !device_ptr || !row_pitch_bytes || r->shard.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
+    *device_ptr = r->shard.d_shard_frame; *row_pitch_bytes = r->shard.shard_frame_bytes / r->shard.height;
+    return WS_OK;
+}
+extern "C" ws_status ws_renderer_shard_download(ws_renderer *r, void *dst_host, void *cuda_stream)
+{
+    if (!r || !dst_host || r->shard.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
+    CU(cudaSetDevice(r->ctx->device));
+    CU(cudaMemcpyAsync(dst_host, r->shard.d_shard_frame, r->shard.shard_frame_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+    return WS_OK;
 }
 
 static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch, const double clear[4],

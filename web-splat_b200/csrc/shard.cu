@@ -25,6 +25,8 @@ namespace {
 
 constexpr int RT_THREADS = 256;
 constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int RT_SPT = 4;                          // slots per thread
+constexpr int RT_PART = RT_THREADS * RT_SPT;       // 1024 local slots per partition
 
 __device__ __forceinline__ bool touches_band(uint2 rect, uint32_t b0, uint32_t b1)
 {
@@ -32,20 +34,40 @@ __device__ __forceinline__ bool touches_band(uint2 rect, uint32_t b0, uint32_t b
     return (w != 0u) && (h != 0u) && (y0 < b1) && (y0 + h > b0);
 }
 
-// ---- pass 1: per 256-slot partition, how many local splats go to each band
+__device__ __forceinline__ void load_rects4(const RouteArgs &a, uint32_t first, uint32_t V, uint2 rc[RT_SPT])
+{
+    if (first + RT_SPT <= V) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a.l_rects + first);       // first is a multiple of 4: 32-B aligned
+        const uint4 u = p[0], v = p[1];
+        rc[0] = make_uint2(u.x, u.y); rc[1] = make_uint2(u.z, u.w); rc[2] = make_uint2(v.x, v.y); rc[3] = make_uint2(v.z, v.w);
+    } else {
+#pragma unroll
+        for (int j = 0; j < RT_SPT; j++) rc[j] = (first + j < V) ? a.l_rects[first + j] : make_uint2(0u, 0u);
+    }
+}
+
+// ---- pass 1: per 1024-slot partition, how many local splats go to each band
 __global__ void __launch_bounds__(RT_THREADS)
 route_count_kernel(RouteArgs a)
 {
+    __shared__ uint32_t s_cnt[8];
     const unsigned tid = threadIdx.x;
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + RT_THREADS - 1u) / RT_THREADS;
+    const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
-        const uint32_t slot = part * RT_THREADS + tid;
-        const uint2 rc = (slot < V) ? a.l_rects[slot] : make_uint2(0u, 0u);
+        if (tid < 8) s_cnt[tid] = 0u;
+        __syncthreads();
+        uint2 rc[RT_SPT];
+        load_rects4(a, part * RT_PART + tid * RT_SPT, V, rc);
         for (uint32_t d = 0; d < a.world; d++) {
-            const uint32_t c = (uint32_t)__syncthreads_count(touches_band(rc, a.band_y0[d], a.band_y0[d + 1]) ? 1 : 0);
-            if (tid == 0) a.part_band_counts[(size_t)part * a.world + d] = c;
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < RT_SPT; j++) c += touches_band(rc[j], a.band_y0[d], a.band_y0[d + 1]) ? 1u : 0u;
+            if (c) atomicAdd(&s_cnt[d], c);           // counts only: order does not matter here
         }
+        __syncthreads();
+        if (tid < a.world) a.part_band_counts[(size_t)part * a.world + tid] = s_cnt[tid];
+        __syncthreads();
     }
 }
 
@@ -57,7 +79,7 @@ route_scan_kernel(RouteArgs a)
     __shared__ uint32_t s_total;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + RT_THREADS - 1u) / RT_THREADS;
+    const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
     const uint32_t per = (nparts + 1023u) / 1024u;
     const uint32_t lo = tid * per, hi = (lo + per < nparts) ? lo + per : nparts;
     for (uint32_t d = 0; d < a.world; d++) {
@@ -98,12 +120,12 @@ route_scan_kernel(RouteArgs a)
 __global__ void __launch_bounds__(RT_THREADS)
 route_scatter_kernel(RouteArgs a)
 {
-    __shared__ uint32_t s_list[RT_THREADS];      // local slots bound for the current band, in slot order
+    __shared__ uint32_t s_list[RT_PART];         // local slots bound for the current band, in slot order
     __shared__ uint32_t s_wcnt[RT_WARPS];
     __shared__ uint32_t s_recv_off[8];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + RT_THREADS - 1u) / RT_THREADS;
+    const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
     if (tid < a.world) {                          // where this rank's records start in each destination
         uint32_t off = 0;
         for (uint32_t s = 0; s < a.rank; s++) off += a.matrix[s * a.world + tid];
@@ -111,36 +133,60 @@ route_scatter_kernel(RouteArgs a)
     }
     __syncthreads();
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
-        const uint32_t slot = part * RT_THREADS + tid;
-        const uint2 rc = (slot < V) ? a.l_rects[slot] : make_uint2(0u, 0u);
+        const uint32_t first = part * RT_PART + tid * RT_SPT;
+        uint2 rc[RT_SPT];
+        load_rects4(a, first, V, rc);
         for (uint32_t d = 0; d < a.world; d++) {
             const uint32_t b0 = a.band_y0[d], b1 = a.band_y0[d + 1];
-            const bool go = touches_band(rc, b0, b1);
-            const unsigned bal = __ballot_sync(0xffffffffu, go);
-            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            bool go[RT_SPT];
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < RT_SPT; j++) { go[j] = touches_band(rc[j], b0, b1); mine += go[j] ? 1u : 0u; }
+            // block exclusive scan of `mine` (slot order = thread order, then j)
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            if (lane == 31) s_wcnt[warp] = incl;
             __syncthreads();
             uint32_t woff = 0, cnt = 0;
 #pragma unroll
             for (int w = 0; w < RT_WARPS; w++) { const uint32_t c = s_wcnt[w]; if (w < (int)warp) woff += c; cnt += c; }
-            if (go) s_list[woff + __popc(bal & lanemask_lt())] = slot;
+            uint32_t pos = woff + incl - mine;
+#pragma unroll
+            for (int j = 0; j < RT_SPT; j++) if (go[j]) s_list[pos++] = first + j;
             __syncthreads();
             const uint32_t dst0 = s_recv_off[d] + a.part_band_bases[(size_t)part * a.world + d];
             if (dst0 + cnt > a.recv_cap) {
                 if (tid == 0 && cnt) atomicOr(a.err, 2u);                       // receiver capacity exceeded: nothing is written
-            } else {
-                uint32_t *ds = a.peer_splats[d];
-                for (uint32_t i = tid; i < cnt * 5u; i += RT_THREADS) {
-                    const uint32_t e = i / 5u, k = i - e * 5u;
-                    ds[(size_t)(dst0 + e) * 5u + k] = a.l_splats[(size_t)s_list[e] * 5u + k];
+            } else if (cnt) {
+                uint32_t *ds = a.peer_splats[d] + (size_t)dst0 * 5u;
+                const uint32_t nw = cnt * 5u;
+                uint32_t i = tid;
+                for (; i + 3u * RT_THREADS < nw; i += 4u * RT_THREADS) {      // four independent gathers in flight per thread
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t ii = i + (uint32_t)u * RT_THREADS, e = ii / 5u, k = ii - e * 5u;
+                        v[u] = a.l_splats[(size_t)s_list[e] * 5u + k];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) ds[i + (uint32_t)u * RT_THREADS] = v[u];
                 }
-                if (tid < cnt) {
-                    const uint32_t src = s_list[tid];
-                    a.peer_keys[d][dst0 + tid] = a.l_keys[src];
+                for (; i < nw; i += RT_THREADS) {
+                    const uint32_t e = i / 5u, k = i - e * 5u;
+                    ds[i] = a.l_splats[(size_t)s_list[e] * 5u + k];
+                }
+                for (uint32_t e = tid; e < cnt; e += RT_THREADS) {
+                    const uint32_t src = s_list[e];
+                    a.peer_keys[d][dst0 + e] = a.l_keys[src];
                     const uint2 r = a.l_rects[src];                            // clip the rectangle to the band's tile rows
                     const uint32_t y0 = r.x >> 16, h = r.y >> 16;
                     const uint32_t ny0 = y0 > b0 ? y0 : b0;
                     const uint32_t ny1 = (y0 + h < b1) ? y0 + h : b1;
-                    a.peer_rects[d][dst0 + tid] = make_uint2((r.x & 0xffffu) | (ny0 << 16), (r.y & 0xffffu) | ((ny1 - ny0) << 16));
+                    a.peer_rects[d][dst0 + e] = make_uint2((r.x & 0xffffu) | (ny0 << 16), (r.y & 0xffffu) | ((ny1 - ny0) << 16));
                 }
             }
             __syncthreads();

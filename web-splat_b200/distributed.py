@@ -60,11 +60,11 @@ class ShardedRenderer:
         L = ws.lib()
         ws._check(L.ws_renderer_shard_configure(self.r._h, self.rank, self.world, int(total_points), pc.num_points(), self.W, self.H))
         self.r._viewport = (self.W, self.H)
-        handles = torch.zeros(192, dtype=torch.uint8)
+        handles = torch.zeros(256, dtype=torch.uint8)
         ws._check(L.ws_renderer_shard_export(self.r._h, C.c_void_p(handles.data_ptr())))
         if self.world > 1:
             dev = torch.device("cuda", torch.cuda.current_device())
-            allh = [torch.zeros(192, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            allh = [torch.zeros(256, dtype=torch.uint8, device=dev) for _ in range(self.world)]
             dist.all_gather(allh, handles.to(dev), group=group)
             allh = torch.cat([h.cpu() for h in allh]).contiguous()
             ws._check(L.ws_renderer_shard_import(self.r._h, C.c_void_p(allh.data_ptr())))
@@ -128,6 +128,52 @@ class ShardedRenderer:
             self.frame_out.copy_(self.band[: self.H])
         mark("assemble")
         return self.frame_out
+
+    def frame_to_root(self, args, clear=(0.0, 0.0, 0.0, 0.0), root=0, host=None, marks=None):
+        """One frame whose bands are stored directly into rank `root`'s assembled frame (peer memory);
+        no image collective, only a barrier.  If `host` (pinned CPU tensor, root only) is given the
+        assembled frame is downloaded into it asynchronously.  Returns nothing: read the frame on the
+        root with download()/ws_renderer_shard_frame after synchronising."""
+        torch, dist, ws = self.torch, self.dist, self.ws
+        L = ws.lib()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def mark(label):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((label, e))
+
+        a = args._c()
+        mark("start")
+        ws._check(L.ws_renderer_shard_begin(self.r._h, self.pc._h, C.byref(a), C.c_void_p(self.row.data_ptr()), stream))
+        mark("stage1+route_count")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.matrix, self.row, group=self.group)
+        else:
+            self.matrix.copy_(self.row)
+        mark("allgather_counts")
+        ws._check(L.ws_renderer_shard_exchange(self.r._h, C.c_void_p(self.matrix.data_ptr()), stream))
+        mark("exchange_kernel")
+        if self.world > 1:
+            dist.all_reduce(self.flag, group=self.group)
+        mark("barrier")
+        ws._check(L.ws_renderer_shard_finish(self.r._h, C.c_void_p(self.matrix.data_ptr()), stream))
+        mark("sort+binning")
+        clr = (C.c_double * 4)(*[float(c) for c in clear])
+        ws._check(L.ws_renderer_render_band_to_root(self.r._h, self.pc._h, root, C.byref(clr), stream))
+        mark("composite_band->root")
+        if self.world > 1:
+            dist.all_reduce(self.flag, group=self.group)                 # all bands have landed in the root's frame
+        mark("barrier2")
+        if host is not None and self.rank == root:
+            ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), stream))
+
+    def download(self, host):
+        """root only: asynchronous copy of the assembled frame into `host` (pinned CPU tensor / numpy array)."""
+        ptr = host.ctypes.data if isinstance(host, np.ndarray) else host.data_ptr()
+        stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        self.ws._check(self.ws.lib().ws_renderer_shard_download(self.r._h, C.c_void_p(ptr), stream))
 
     def stats(self, allow_overflow=False):
         return self.r.stats(allow_overflow)
