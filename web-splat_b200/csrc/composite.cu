@@ -35,14 +35,52 @@ __device__ __forceinline__ float hhi(uint32_t w) { __half_raw r; r.x = (unsigned
 // MUFU.EX2: the argument is in [-6.8, 0], far from the denormal range, so .ftz is exact enough
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+struct RawSplat { uint32_t w[5]; };
+
+// staged form of one splat, in pixel coordinates relative to the tile CENTRE (u, v in [-7.5, 7.5]):
+//   A = {q0, q1, q2, q3}   B = {q4, q5, alpha, r}   C = {g, b, | cx, cy, ex, ey in D}
+// a * log2(e) = q0 + q1 u + q2 v + q3 u^2 + q4 u v + q5 v^2  (five FMAs per pixel); the quadratic form
+// is S = log2(e) * Binv^T Binv of the pixel-space map [dx;dy] = Bm p.  Centring on the tile keeps the
+// cancellation error of the expanded form below ~6e-5 in `a` even for the smallest footprints
+// (sigma^2 = kernel_size), inside the parity tolerance window.
+__device__ __forceinline__ void decode_splat(const RawSplat &rs, float fw, float fh, float hw, float hh, float ox, float oy,
+                                             float4 &A, float4 &B, float4 &C, float4 &D)
+{
+    const float v1x = hlo(rs.w[0]), v1y = hhi(rs.w[0]), v2x = hlo(rs.w[1]), v2y = hhi(rs.w[1]);
+    const float ccx = hlo(rs.w[2]), ccy = hhi(rs.w[2]);
+    // pixel-space map  [dx;dy] = Bm p,  Bm = [[W v1x, W v2x],[-H v1y, -H v2y]]  (y down)
+    const float b00 = fw * v1x, b01 = fw * v2x, b10 = -(fh * v1y), b11 = -(fh * v2y);   // exact products
+    const float det = b00 * b11 - b01 * b10;
+    const float inv = SQRT_LOG2E / det;
+    const float i00 = b11 * inv, i01 = -b01 * inv, i10 = -b10 * inv, i11 = b00 * inv;  // sqrt(log2 e) * Binv
+    const float s00 = i00 * i00 + i10 * i10, s01 = i00 * i01 + i10 * i11, s11 = i01 * i01 + i11 * i11;
+    const float cx = ccx * hw + ox;              // centre relative to the tile centre (exact product + 1 rounding)
+    const float cy = oy - ccy * hh;
+    const float tx = s00 * cx + s01 * cy, ty = s01 * cx + s11 * cy;                    // S c
+    A.x = tx * cx + ty * cy;                     // q0 = c^T S c
+    A.y = -2.f * tx;                             // q1
+    A.z = -2.f * ty;                             // q2
+    A.w = s00;                                   // q3
+    B.x = 2.f * s01;                             // q4
+    B.y = s11;                                   // q5
+    B.z = hhi(rs.w[4]);                          // alpha
+    B.w = hlo(rs.w[3]);                          // r
+    C.x = hhi(rs.w[3]); C.y = hlo(rs.w[4]);      // g, b
+    C.z = 0.f; C.w = 0.f;
+    D.x = cx; D.y = cy;
+    D.z = FOOTPRINT_R * (fw * sqrtf(v1x * v1x + v2x * v2x)) + RECT_PAD;
+    D.w = FOOTPRINT_R * (fh * sqrtf(v1y * v1y + v2y * v2y)) + RECT_PAD;
+}
+
 template <int FORMAT>
 __global__ void __launch_bounds__(CB_THREADS)
 composite_kernel(CompositeArgs a)
 {
-    // staged splats, SoA as three float4 planes + bbox plane
-    __shared__ float4 s_a[CB_BATCH];   // cx, cy (relative to tile origin, pixel units), i00, i01
-    __shared__ float4 s_b[CB_BATCH];   // i10, i11, alpha, r
-    __shared__ float4 s_c[CB_BATCH];   // g, b, ex, ey
+    // double-buffered staging: batch b+1 is fetched (global gathers) while batch b is evaluated
+    __shared__ float4 s_a[2][CB_BATCH];
+    __shared__ float4 s_b[2][CB_BATCH];
+    __shared__ float2 s_c[2][CB_BATCH];
+    __shared__ float4 s_d[2][CB_BATCH];              // bounding box for the per-warp cull
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = a.uniforms->width, H = a.uniforms->height;
@@ -53,87 +91,96 @@ composite_kernel(CompositeArgs a)
     if (range.y <= range.x) range.x = range.y = 0u;      // untouched tile
     const float fw = (float)W, fh = (float)H;
     const float hw = 0.5f * fw, hh = 0.5f * fh;
-    const float ox = hw - (float)(tile_x * TILE), oy = hh - (float)(tile_y * TILE);   // exact
+    const float ox = hw - (float)(tile_x * TILE + TILE / 2), oy = hh - (float)(tile_y * TILE + TILE / 2);   // exact
 
     // warp's 8x4 pixel block inside the tile
     const uint32_t bx = (warp & 1u) * 8u, by = (warp >> 1) * 4u;
     const uint32_t lx = bx + (lane & 7u), ly = by + (lane >> 3);
     const uint32_t px = tile_x * TILE + lx, py = tile_y * TILE + ly;
     const bool inside = (px < W) && (py < H);
-    const float fx = (float)lx + 0.5f, fy = (float)ly + 0.5f;
-    // block bounds in pixel-centre coordinates relative to the tile origin
-    const float blo_x = (float)bx + 0.5f, bhi_x = (float)bx + 7.5f;
-    const float blo_y = (float)by + 0.5f, bhi_y = (float)by + 3.5f;
+    const float fx = (float)lx - 7.5f, fy = (float)ly - 7.5f;          // pixel centre relative to the tile centre
+    const float fxx = fx * fx, fxy = fx * fy, fyy = fy * fy;
+    // block bounds in pixel-centre coordinates relative to the tile centre
+    const float blo_x = (float)bx - 7.5f, bhi_x = (float)bx - 0.5f;
+    const float blo_y = (float)by - 7.5f, bhi_y = (float)by - 4.5f;
 
     float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
     bool done = !inside;
 
     int32_t remaining = (int32_t)(range.y - range.x);
     uint32_t cursor = range.y;           // walk from the end: nearest first
-    while (remaining > 0) {
-        const bool warp_done = __all_sync(0xffffffffu, done);
-        if (__syncthreads_and(warp_done ? 1 : 0)) break;
 
-        const int cnt = remaining < CB_BATCH ? remaining : CB_BATCH;
+    auto fetch = [&](RawSplat &rs, uint32_t cur, int cnt) {
         if ((int)tid < cnt) {
-            const uint32_t slot = a.pair_slots[cursor - 1u - tid];
+            const uint32_t slot = __ldg(a.pair_slots + (cur - 1u - tid));
             const uint32_t *sp = a.splats + (size_t)slot * 5u;
-            const uint32_t w0 = __ldg(sp), w1 = __ldg(sp + 1), w2 = __ldg(sp + 2), w3 = __ldg(sp + 3), w4 = __ldg(sp + 4);
-            const float v1x = hlo(w0), v1y = hhi(w0), v2x = hlo(w1), v2y = hhi(w1);
-            const float ccx = hlo(w2), ccy = hhi(w2);
-            // pixel-space map  [dx;dy] = B p,  B = [[W v1x, W v2x],[-H v1y, -H v2y]]  (y down)
-            const float b00 = fw * v1x, b01 = fw * v2x, b10 = -(fh * v1y), b11 = -(fh * v2y);   // exact products
-            const float det = b00 * b11 - b01 * b10;
-            const float inv = SQRT_LOG2E / det;          // fold log2(e) into p so that exp(-a) = exp2(-a')
-            float4 A, B, C;
-            A.x = ccx * hw + ox;                         // centre relative to the tile origin (exact product + 1 rounding)
-            A.y = oy - ccy * hh;
-            A.z = b11 * inv;  A.w = -b01 * inv;
-            B.x = -b10 * inv; B.y = b00 * inv;
-            B.z = hhi(w4);                               // alpha
-            B.w = hlo(w3);                               // r
-            C.x = hhi(w3); C.y = hlo(w4);                // g, b
-            C.z = FOOTPRINT_R * (fw * sqrtf(v1x * v1x + v2x * v2x)) + RECT_PAD;
-            C.w = FOOTPRINT_R * (fh * sqrtf(v1y * v1y + v2y * v2y)) + RECT_PAD;
-            s_a[tid] = A; s_b[tid] = B; s_c[tid] = C;
+#pragma unroll
+            for (int q = 0; q < 5; q++) rs.w[q] = __ldg(sp + q);
         }
-        __syncthreads();
+    };
+
+    RawSplat nxt;
+    int cnt = remaining < CB_BATCH ? remaining : CB_BATCH;
+    fetch(nxt, cursor, cnt);
+    int buf = 0;
+    while (remaining > 0) {
+        // publish the fetched batch
+        if ((int)tid < cnt) {
+            float4 A, B, C, D;
+            decode_splat(nxt, fw, fh, hw, hh, ox, oy, A, B, C, D);
+            s_a[buf][tid] = A; s_b[buf][tid] = B; s_c[buf][tid] = make_float2(C.x, C.y); s_d[buf][tid] = D;
+        }
+        const bool warp_done = __all_sync(0xffffffffu, done);
+        // one barrier per batch: makes the batch visible and agrees on the tile-level early-out.  Buffer
+        // `buf` was last read two batches ago, and every warp has passed the previous barrier since.
+        if (__syncthreads_and(warp_done ? 1 : 0)) break;
+        const int cur_cnt = cnt;
+        remaining -= cur_cnt;
+        cursor -= (uint32_t)cur_cnt;
+        cnt = remaining < CB_BATCH ? remaining : CB_BATCH;
+        if (remaining > 0) fetch(nxt, cursor, cnt);          // in flight while this batch is evaluated
 
         if (!warp_done) {
-            for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const float4 *sa = s_a[buf], *sb = s_b[buf], *sd = s_d[buf];
+            const float2 *sc = s_c[buf];
+            // one pixel-splat evaluation: 5 FMAs for a*log2(e), MUFU.EX2, blend
+#define WS_EVAL(J)                                                                              \
+            {                                                                                   \
+                const float4 A = sa[J];                                                         \
+                const float4 B = sb[J];                                                         \
+                float aa = fmaf(A.y, fx, A.x);                                                  \
+                aa = fmaf(A.z, fy, aa); aa = fmaf(A.w, fxx, aa); aa = fmaf(B.x, fxy, aa); aa = fmaf(B.y, fyy, aa); \
+                if (!done && aa <= TWO_CUTOFF * LOG2E) {                                        \
+                    const float2 C = sc[J];                                                     \
+                    const float wt = fminf(0.99f, ex2_approx(-aa) * B.z) * T;                   \
+                    cr = fmaf(B.w, wt, cr); cg = fmaf(C.x, wt, cg); cb = fmaf(C.y, wt, cb);     \
+                    T -= wt;                                      /* T * (1 - w) */             \
+                    if (T < T_EPS) done = true;                                                 \
+                }                                                                               \
+            }
+            for (int c0 = 0; c0 < cur_cnt; c0 += 32) {
                 const int k = c0 + (int)lane;
                 bool hit = false;
-                if (k < cnt) {
-                    const float4 A = s_a[k];
-                    const float4 C = s_c[k];
-                    hit = (A.x + C.z >= blo_x) && (A.x - C.z <= bhi_x) && (A.y + C.w >= blo_y) && (A.y - C.w <= bhi_y);
+                if (k < cur_cnt) {
+                    const float4 D = sd[k];
+                    hit = (D.x + D.z >= blo_x) && (D.x - D.z <= bhi_x) && (D.y + D.w >= blo_y) && (D.y - D.w <= bhi_y);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int j = c0 + (__ffs(m) - 1);
+                while (m) {                                             // two hits per trip: front-to-back order is kept
+                    const int j0 = c0 + (__ffs(m) - 1);
                     m &= m - 1u;
-                    const float4 A = s_a[j];
-                    const float4 B = s_b[j];
-                    const float dx = fx - A.x, dy = fy - A.y;
-                    const float p0 = A.z * dx + A.w * dy;
-                    const float p1 = B.x * dx + B.y * dy;
-                    const float aa = p0 * p0 + p1 * p1;                 // = a * log2(e)
-                    if (!done && aa <= TWO_CUTOFF * LOG2E) {
-                        const float4 C = s_c[j];
-                        float wgt = ex2_approx(-aa) * B.z;
-                        wgt = fminf(0.99f, wgt);
-                        const float wt = wgt * T;
-                        cr += B.w * wt; cg += C.x * wt; cb += C.y * wt;
-                        T *= (1.f - wgt);
-                        if (T < T_EPS) done = true;
+                    WS_EVAL(j0)
+                    if (m) {
+                        const int j1 = c0 + (__ffs(m) - 1);
+                        m &= m - 1u;
+                        WS_EVAL(j1)
                     }
                 }
                 if (__all_sync(0xffffffffu, done)) break;
             }
+#undef WS_EVAL
         }
-        remaining -= cnt;
-        cursor -= (uint32_t)cnt;
-        // next iteration's __syncthreads_and orders these smem reads before the restaging
+        buf ^= 1;
     }
 
     if (inside) {
