@@ -68,7 +68,7 @@ __device__ __forceinline__ void lookback_level(const uint32_t *col, int p, int l
 }
 
 template <bool EMIT_RANGES>
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, 3)   // 16 items x 3 CTAs/SM measured best: 8 items x 4 CTAs and 16 items x 4 CTAs (spilling) were 7-10 % slower
 onesweep_pass_kernel(SortPassArgs a)
 {
     __shared__ uint32_t s_keys[SORT_PART];      // during ranking the first 8 KB double as the peer masks
