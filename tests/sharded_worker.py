@@ -49,6 +49,16 @@ def main():
                 same2 = torch.equal(host, ref.cpu())
                 ok = ok and same2
                 print("   to_root identical=%s" % same2, flush=True)
+            # and the variant without any host-side collective (mailbox flags in peer memory), several frames back to back
+            for rep in range(3):
+                if rank == 0:
+                    host.zero_()
+                sh.frame_peer(args, clear=(0.1, 0.2, 0.3, 0.5), root=0, host=host)
+            torch.cuda.synchronize()
+            if rank == 0:
+                same3 = torch.equal(host, ref.cpu())
+                ok = ok and same3
+                print("   peer-mailbox identical=%s" % same3, flush=True)
             dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

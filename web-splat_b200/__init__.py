@@ -124,6 +124,7 @@ EXPORTED_SYMBOLS = [
     "ws_renderer_shard_configure", "ws_renderer_shard_export", "ws_renderer_shard_import", "ws_renderer_shard_begin",
     "ws_renderer_shard_exchange", "ws_renderer_shard_finish", "ws_renderer_shard_band", "ws_renderer_render_band",
     "ws_renderer_render_band_to_root", "ws_renderer_shard_frame", "ws_renderer_shard_download",
+    "ws_renderer_shard_frame_to_root",
 ]
 
 _lib = None
@@ -194,6 +195,7 @@ def lib():
         "ws_renderer_render_band_to_root": (i32, [vp, vp, u32, C.POINTER(C.c_double * 4), vp]),
         "ws_renderer_shard_frame": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "ws_renderer_shard_download": (i32, [vp, vp, vp]),
+        "ws_renderer_shard_frame_to_root": (i32, [vp, vp, C.POINTER(ws_splatting_args), u32, C.POINTER(C.c_double * 4), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -292,6 +292,9 @@ struct ShardState {
     uint32_t *peer_splats[8] = {}, *peer_keys[8] = {}; uint2 *peer_rects[8] = {};
     uint8_t *peer_frame[8] = {};               // every rank's assembled-frame buffer (only the root's is written)
     uint8_t *d_shard_frame = nullptr; size_t shard_frame_bytes = 0;
+    ShardMailbox *d_mail = nullptr, *peer_mail[8] = {};   // rows / barrier / band flags written by the peers
+    uint32_t epoch = 0;
+    uint32_t *pending_signal = nullptr;        // set for the next band composite only
     bool opened[8] = {};
     bool imported = false;
     int phase = 0;
@@ -621,11 +624,11 @@ static void free_shard(ws_renderer *r)
     for (int p = 0; p < 8; p++) {
         if (s.opened[p]) {
             cudaIpcCloseMemHandle(s.peer_splats[p]); cudaIpcCloseMemHandle(s.peer_keys[p]); cudaIpcCloseMemHandle(s.peer_rects[p]);
-            cudaIpcCloseMemHandle(s.peer_frame[p]);
+            cudaIpcCloseMemHandle(s.peer_frame[p]); cudaIpcCloseMemHandle(s.peer_mail[p]);
             s.opened[p] = false;
         }
     }
-    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame);
+    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame); cudaFree(s.d_mail);
     s = ShardState();
 }
 
@@ -654,19 +657,22 @@ extern "C" ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, 
     s.part_band_counts = s.d_route; s.part_band_bases = s.d_route + parts * world; s.hist_dummy = s.d_route + parts * world * 2;
     s.shard_frame_bytes = (size_t)width * height * (r->format == WS_FORMAT_RGBA8_UNORM ? 4 : (r->format == WS_FORMAT_RGBA16_FLOAT ? 8 : 16));
     CU(cudaMalloc(&s.d_shard_frame, s.shard_frame_bytes));
+    CU(cudaMalloc(&s.d_mail, sizeof(ShardMailbox)));
+    CU(cudaMemset(s.d_mail, 0, sizeof(ShardMailbox)));
     s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects; s.peer_frame[rank] = s.d_shard_frame;
+    s.peer_mail[rank] = s.d_mail;
     return WS_OK;
 }
 
-extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_4x64)
+extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_5x64)
 {
-    void *handles_3x64 = handles_4x64;
+    void *handles_3x64 = handles_5x64;
     if (!r || !handles_3x64) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (r->shard.world < 1 || !r->d_splats) return fail(WS_ERR_INVALID_ARGUMENT, "call ws_renderer_shard_configure first");
     CU(cudaSetDevice(r->ctx->device));
-    cudaIpcMemHandle_t h[4];
+    cudaIpcMemHandle_t h[5];
     CU(cudaIpcGetMemHandle(&h[0], r->d_splats)); CU(cudaIpcGetMemHandle(&h[1], r->d_keys[0])); CU(cudaIpcGetMemHandle(&h[2], r->d_rects));
-    CU(cudaIpcGetMemHandle(&h[3], r->shard.d_shard_frame));
+    CU(cudaIpcGetMemHandle(&h[3], r->shard.d_shard_frame)); CU(cudaIpcGetMemHandle(&h[4], r->shard.d_mail));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(handles_3x64, h, sizeof h);
     return WS_OK;
@@ -681,11 +687,13 @@ extern "C" ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_ha
     const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
     for (uint32_t p = 0; p < s.world; p++) {
         if (p == s.rank || s.opened[p]) continue;
-        void *a = nullptr, *b = nullptr, *c = nullptr, *f = nullptr;
-        CU(cudaIpcOpenMemHandle(&a, h[p * 4 + 0], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&b, h[p * 4 + 1], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&c, h[p * 4 + 2], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&f, h[p * 4 + 3], cudaIpcMemLazyEnablePeerAccess));
+        void *a = nullptr, *b = nullptr, *c = nullptr, *f = nullptr, *m = nullptr;
+        CU(cudaIpcOpenMemHandle(&a, h[p * 5 + 0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&b, h[p * 5 + 1], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c, h[p * 5 + 2], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&f, h[p * 5 + 3], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&m, h[p * 5 + 4], cudaIpcMemLazyEnablePeerAccess));
+        s.peer_mail[p] = static_cast<ShardMailbox *>(m);
         s.peer_splats[p] = static_cast<uint32_t *>(a); s.peer_keys[p] = static_cast<uint32_t *>(b); s.peer_rects[p] = static_cast<uint2 *>(c);
         s.peer_frame[p] = static_cast<uint8_t *>(f);
         s.opened[p] = true;
@@ -704,6 +712,8 @@ static void fill_route_args(ws_renderer *r, RouteArgs &a)
     a.totals = nullptr; a.matrix = nullptr;
     for (int p = 0; p < 8; p++) { a.peer_splats[p] = s.peer_splats[p]; a.peer_keys[p] = s.peer_keys[p]; a.peer_rects[p] = s.peer_rects[p]; }
     a.recv_cap = s.recv_cap; a.err = &r->d_counters->error_flags;
+    for (int p = 0; p < 8; p++) a.peer_mail[p] = nullptr;          // NCCL mode unless the caller fills these in
+    a.epoch = 0; a.done_counter = &r->d_counters->scatter_done;
 }
 
 extern "C" ws_status ws_renderer_shard_begin(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
@@ -771,6 +781,66 @@ extern "C" ws_status ws_renderer_shard_finish(ws_renderer *r, const uint32_t *ma
     r->prepared = true;
     r->last_stream = stream;
     s.phase = 0;
+    return WS_OK;
+}
+
+static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch, const double clear[4],
+                             void *cuda_stream, uint32_t tile_y0, uint32_t tile_rows);
+
+// The whole sharded frame in ONE call and with NO host-side collective: the count rows, the barrier
+// after the exchange and the "band has landed" signal are epoch flags that the kernels themselves
+// write into the peers' mailboxes (release / acquire at system scope over NVLink).  The frame ends up
+// assembled in rank `root`'s frame buffer (ws_renderer_shard_frame / _download); on the root the call
+// also enqueues the wait for all bands.  Every rank must call it once per frame, in the same order.
+extern "C" ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
+                                                     uint32_t root, const double clear[4], void *cuda_stream)
+{
+    ws_status st = validate_frame(r, pc, args);
+    if (st != WS_OK) return st;
+    ShardState &s = r->shard;
+    if (s.world < 1 || root >= s.world) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding / bad root");
+    if (s.world > 1 && !s.imported) return fail(WS_ERR_INVALID_ARGUMENT, "peer handles not imported");
+    if (args->viewport[0] != s.width || args->viewport[1] != s.height) return fail(WS_ERR_INVALID_ARGUMENT, "viewport differs from ws_renderer_shard_configure");
+    if (pc->n > s.local_cap) return fail(WS_ERR_INVALID_ARGUMENT, "local shard larger than configured");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    st = begin_frame(r, pc, args, s.recv_cap, stream);
+    if (st != WS_OK) return st;
+    s.epoch += 1;
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
+    {   // stage 1 on the local shard
+        PreprocessArgs a;
+        a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
+        a.uniforms = r->d_uniforms;
+        a.splats = s.l_splats; a.depth_keys = s.l_keys; a.slot_vals = s.l_vals; a.rects = s.l_rects;
+        a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
+        a.hist = s.hist_dummy; a.counters = r->d_counters;
+        CU(cudaMemsetAsync(s.hist_dummy, 0, 4 * 256 * 4, stream));
+        CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
+    }
+    RouteArgs ra; fill_route_args(r, ra);
+    for (uint32_t p = 0; p < s.world; p++) ra.peer_mail[p] = s.peer_mail[p];
+    ra.epoch = s.epoch;
+    CU(launch_route_count(ra, r->ctx->sm_count * 8, stream));          // counts + scan; the row goes to every rank's mailbox
+    CU(launch_route_scatter(ra, r->ctx->sm_count * 8, stream));        // waits for all rows, stores the splats into the owners' buffers
+    CU(launch_shard_finish_peer(ra, r->d_vals[0], r->d_keys[0], r->d_hist_depth, r->depth_passes, r->d_counters,
+                                r->ctx->sm_count * 4, stream));        // waits for every rank's exchange flag
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
+    st = enqueue_stage2(r, stream);
+    if (st != WS_OK) return st;
+    r->prepared = true; r->last_stream = stream; r->last_n = pc->n;
+    // stage 3: pixels go straight into the root's frame; the last CTA raises this rank's band flag there
+    const size_t pitch = s.shard_frame_bytes / s.height;
+    const uint32_t first = s.band_y0[s.rank] * TILE;
+    const uint32_t rows = s.band_y0[s.rank + 1] - s.band_y0[s.rank];
+    if (rows > 0 && first < s.height) {
+        s.pending_signal = &s.peer_mail[root]->flag_band[s.rank];
+        st = render_rows(r, pc, s.peer_frame[root] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], rows);
+        if (st != WS_OK) return st;
+    } else {
+        return fail(WS_ERR_UNSUPPORTED, "a rank without tile rows (more ranks than tile rows) is not supported");
+    }
+    if (s.rank == root) CU(launch_wait_bands(s.d_mail, s.world, s.epoch, &r->d_counters->error_flags, stream));
     return WS_OK;
 }
 
@@ -849,6 +919,8 @@ static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_
     a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
     a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
     a.tile_y0 = tile_y0;
+    a.signal_flag = r->shard.pending_signal; a.signal_epoch = r->shard.epoch; a.done_counter = &r->d_counters->composite_done;
+    r->shard.pending_signal = nullptr;
     for (int i = 0; i < 4; i++) a.clear[i] = clear ? (float)clear[i] : 0.f;
     if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND0], stream));
     if (tile_rows) CU(launch_composite(a, U.tiles_x, tile_rows, stream));

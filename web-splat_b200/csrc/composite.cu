@@ -198,6 +198,16 @@ composite_kernel(CompositeArgs a)
             reinterpret_cast<uint32_t *>(row)[px] = r8 | (g8 << 8) | (b8 << 16) | (a8 << 24);
         }
     }
+    if (a.signal_flag) {
+        // sharded rendering: the pixels above went to the ROOT GPU's frame (peer memory); the last CTA
+        // of this band raises the band flag there once every store is fenced at system scope
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t prev = atomicAdd(a.done_counter, 1u);
+            if (prev == gridDim.x * gridDim.y - 1u) { __threadfence_system(); st_release_sys(a.signal_flag, a.signal_epoch); }
+        }
+    }
 }
 
 }  // namespace

@@ -70,7 +70,7 @@ struct ShRaw {
     __device__ __forceinline__ V3 coef(int k) const { return V3{h(k * 3), h(k * 3 + 1), h(k * 3 + 2)}; }
 };
 struct ShQuant {
-    const int8_t *p;                // entry base: (sh_idx * ncoef) * 3 bytes
+    uint32_t w[12];                 // the entry's (file_deg+1)^2*3 i8 bytes, dc first (io/npz.rs:183-196), zero padded
     Quant dc, rest;
     __device__ __forceinline__ float dq(int8_t b, const Quant &q) const
     {
@@ -79,10 +79,29 @@ struct ShQuant {
         float v = sn * 127.f;
         return (v - (float)q.zero_point) * q.scale;   // dequantizef4
     }
+    __device__ __forceinline__ int8_t byte(int i) const { return (int8_t)((w[i >> 2] >> ((i & 3) * 8)) & 0xffu); }
     __device__ __forceinline__ V3 coef(int k) const
     {
         const Quant &q = (k == 0) ? dc : rest;
-        return V3{dq(p[k * 3], q), dq(p[k * 3 + 1], q), dq(p[k * 3 + 2], q)};
+        return V3{dq(byte(k * 3), q), dq(byte(k * 3 + 1), q), dq(byte(k * 3 + 2), q)};
+    }
+    // entry base = sh_idx * ncoef * 3 bytes; degree-3 entries (48 B) are 16-B aligned: three 128-bit loads
+    __device__ __forceinline__ void load(const uint8_t *base, uint32_t sh_idx, uint32_t ncoef)
+    {
+        const uint8_t *p = base + (size_t)sh_idx * ncoef * 3u;
+        if (ncoef == 16u) {
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(p);
+            const uint4 a = __ldg(q4), b = __ldg(q4 + 1), c = __ldg(q4 + 2);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; i++) w[i] = 0u;
+            const uint32_t nb = ncoef * 3u;                    // 3, 12 or 27 bytes
+#pragma unroll
+            for (int i = 0; i < 27; i++)                       // static indices keep w[] in registers
+                if ((uint32_t)i < nb) w[i >> 2] |= (uint32_t)__ldg(p + i) << ((i & 3) * 8);
+        }
     }
 };
 
@@ -521,7 +540,7 @@ preprocess_kernel(PreprocessArgs a)
                                            half_hi(w1) * s2, half_lo(w2) * s2, half_hi(w2) * s2};
                     const uint32_t ncoef = (U.file_sh_deg + 1u) * (U.file_sh_deg + 1u);
                     ShQuant sh;
-                    sh.p = reinterpret_cast<const int8_t *>(a.sh_coefs) + (size_t)sh_idx * ncoef * 3u;
+                    sh.load(a.sh_coefs, sh_idx, ncoef);
                     sh.dc = U.quant.color_dc; sh.rest = U.quant.color_rest;
                     project_tail<true>(U, x, y, z, cs[0], cs[1], cs[2], pp[0], pp[1], pp[2], pp[3], cov6, opacity, sh, o);
                 }

@@ -77,6 +77,7 @@ route_scan_kernel(RouteArgs a)
 {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_total;
+    __shared__ uint32_t s_tot[8];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
     const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
@@ -111,8 +112,19 @@ route_scan_kernel(RouteArgs a)
             a.part_band_bases[(size_t)i * a.world + d] = run;
             run += c;
         }
-        if (tid == 0) a.totals[d] = (nparts > 0u) ? s_total : 0u;
+        if (tid == 0) { const uint32_t t = (nparts > 0u) ? s_total : 0u; if (a.totals) a.totals[d] = t; s_tot[d] = t; }
         __syncthreads();
+    }
+    if (a.peer_mail[a.rank]) {
+        // publish this rank's row into EVERY rank's mailbox, then raise the row flag (release, system scope)
+        const uint32_t par = a.epoch & 1u;
+        if (tid < a.world * a.world) {
+            const uint32_t p = tid / a.world, d = tid - p * a.world;
+            a.peer_mail[p]->matrix[par][a.rank * a.world + d] = s_tot[d];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < a.world) st_release_sys(&a.peer_mail[tid]->flag_rows[a.rank], a.epoch);
     }
 }
 
@@ -126,9 +138,15 @@ route_scatter_kernel(RouteArgs a)
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
     const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
+    const uint32_t *matrix = a.matrix;
+    if (a.peer_mail[a.rank]) {                    // mailbox mode: wait until every rank's count row of this frame has arrived
+        if (tid < a.world) wait_epoch(&a.peer_mail[a.rank]->flag_rows[tid], a.epoch, a.err);
+        __syncthreads();
+        matrix = a.peer_mail[a.rank]->matrix[a.epoch & 1u];
+    }
     if (tid < a.world) {                          // where this rank's records start in each destination
         uint32_t off = 0;
-        for (uint32_t s = 0; s < a.rank; s++) off += a.matrix[s * a.world + tid];
+        for (uint32_t s = 0; s < a.rank; s++) off += matrix[s * a.world + tid];
         s_recv_off[tid] = off;
     }
     __syncthreads();
@@ -192,6 +210,18 @@ route_scatter_kernel(RouteArgs a)
             __syncthreads();
         }
     }
+    if (a.peer_mail[a.rank]) {
+        // the last CTA to finish tells every rank that this rank's records have landed
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t prev = atomicAdd(a.done_counter, 1u);
+            if (prev == gridDim.x - 1u) {
+                __threadfence_system();
+                for (uint32_t p = 0; p < a.world; p++) st_release_sys(&a.peer_mail[p]->flag_xchg[a.rank], a.epoch);
+            }
+        }
+    }
 }
 
 // ---- after the exchange: V' = records received; payload iota for the depth sort
@@ -213,7 +243,51 @@ __global__ void shard_set_visible_kernel(const uint32_t *matrix, uint32_t world,
     counters->num_visible = v;
 }
 
+// peer mode: wait for every rank's exchange flag, then V', payload iota and the depth-key digit histograms in one kernel
+__global__ void __launch_bounds__(256)
+shard_finish_peer_kernel(RouteArgs a, uint32_t *vals, const uint32_t *__restrict__ keys, uint32_t *hist, int passes, FrameCounters *counters)
+{
+    __shared__ uint32_t s_hist[4 * 256];
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < 4u * 256u; i += 256u) s_hist[i] = 0u;
+    const ShardMailbox *mail = a.peer_mail[a.rank];
+    if (tid < a.world) wait_epoch(&mail->flag_xchg[tid], a.epoch, a.err);
+    __syncthreads();
+    const uint32_t *matrix = mail->matrix[a.epoch & 1u];
+    uint32_t v = 0;
+    for (uint32_t s = 0; s < a.world; s++) v += matrix[s * a.world + a.rank];
+    if (v > a.recv_cap) { v = a.recv_cap; if (blockIdx.x == 0 && tid == 0) atomicOr(a.err, 2u); }
+    for (uint32_t i = blockIdx.x * 256u + tid; i < v; i += gridDim.x * 256u) {
+        vals[i] = i;
+        const uint32_t k = keys[i];
+        for (int d = 0; d < passes; d++) atomicAdd(&s_hist[d * 256 + ((k >> (8 * d)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < (unsigned)passes * 256u; i += 256u) { const uint32_t c = s_hist[i]; if (c) atomicAdd(hist + i, c); }
+    if (blockIdx.x == 0 && tid == 0) { counters->num_local_visible = counters->num_visible; counters->num_visible = v; }
+}
+
+// root only: the assembled frame is complete once every rank's band flag has reached the epoch
+__global__ void wait_bands_kernel(const ShardMailbox *mail, uint32_t world, uint32_t epoch, uint32_t *err)
+{
+    if (threadIdx.x < world) wait_epoch(&mail->flag_band[threadIdx.x], epoch, err);
+}
+
 }  // namespace
+
+cudaError_t launch_shard_finish_peer(const RouteArgs &a, uint32_t *vals, const uint32_t *keys, uint32_t *hist, int passes,
+                                     FrameCounters *counters, int grid, cudaStream_t stream)
+{
+    // NOTE: counters->num_visible is rewritten by block 0 while other blocks of this kernel never read it
+    shard_finish_peer_kernel<<<grid, 256, 0, stream>>>(a, vals, keys, hist, passes, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wait_bands(const ShardMailbox *mail, uint32_t world, uint32_t epoch, uint32_t *err, cudaStream_t stream)
+{
+    wait_bands_kernel<<<1, 32, 0, stream>>>(mail, world, epoch, err);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream)
 {

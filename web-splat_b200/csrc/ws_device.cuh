@@ -46,7 +46,9 @@ struct FrameCounters {
     uint32_t error_flags;       // bit 0: a look-back spin exceeded SPIN_LIMIT (never expected)
     uint32_t ticket[12];        // dynamic partition tickets: [2..5] depth passes, [6..8] tile passes
     uint32_t num_local_visible; // sharded mode: survivors of the local shard (num_visible then counts the received ones)
-    uint32_t _r1[3];
+    uint32_t scatter_done;      // sharded mode: CTAs of the exchange kernel that have finished (last one signals the peers)
+    uint32_t composite_done;    // sharded mode: CTAs of the band compositor that have finished
+    uint32_t _r1[1];
 };
 
 constexpr int TILE = 16;                    // 16x16 pixel tiles
@@ -146,6 +148,37 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// ---- cross-GPU signalling through peer-mapped memory (NVLink): release/acquire at system scope ----
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag has reached `epoch` (epochs only grow; wrap-safe signed difference)
+__device__ __forceinline__ bool wait_epoch(const uint32_t *flag, uint32_t epoch, uint32_t *err)
+{
+    for (uint32_t spins = 0; (int32_t)(ld_acquire_sys(flag) - epoch) < 0; ++spins) {
+        if (spins > (SPIN_LIMIT << 2)) { if (err) atomicOr(err, 4u); return false; }   // ~1 s: a peer never arrived
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// Per-rank mailbox other ranks write into (sharded frame without host-side collectives).
+// Double buffered by frame parity: a fast rank can be at most one frame ahead of a slow one.
+struct ShardMailbox {
+    uint32_t matrix[2][64];     // [parity][src * world + dst]: splats of rank src that touch band dst
+    uint32_t flag_rows[8];      // epoch of the last count row received from each source rank
+    uint32_t flag_xchg[8];      // epoch whose exchange stores from each source rank have landed
+    uint32_t flag_band[8];      // epoch whose band pixels from each rank have landed (read on the root)
+    uint32_t _pad[104];
+};
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {

@@ -7,6 +7,7 @@ namespace ws {
 
 struct FrameUniforms;
 struct FrameCounters;
+struct ShardMailbox;
 
 // ---- stage 1 -----------------------------------------------------------------
 struct PreprocessArgs {
@@ -78,6 +79,9 @@ struct CompositeArgs {
     int format;                   // ws_format
     float clear[4];
     uint32_t tile_y0;             // first tile row to composite (sharded rendering: this rank's band); dst row 0 = that row
+    uint32_t *signal_flag;        // optional (peer-mapped): set to signal_epoch by the last CTA once every pixel store is fenced
+    uint32_t signal_epoch;
+    uint32_t *done_counter;       // with signal_flag: zeroed per frame
 };
 cudaError_t launch_composite(const CompositeArgs &a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream);
 
@@ -93,7 +97,14 @@ struct RouteArgs {
     uint32_t *peer_splats[8], *peer_keys[8]; uint2 *peer_rects[8];   // destination buffers (peer-mapped for other ranks)
     uint32_t recv_cap;
     uint32_t *err;
+    // host-collective-free mode: rows, barrier and band signal go through peer-mapped mailboxes
+    ShardMailbox *peer_mail[8];                                // NULL: NCCL mode (matrix/totals are plain buffers)
+    uint32_t epoch;                                            // frame number, > 0
+    uint32_t *done_counter;                                    // zeroed per frame: last-CTA detection
 };
+cudaError_t launch_shard_finish_peer(const RouteArgs &a, uint32_t *vals, const uint32_t *keys, uint32_t *hist, int passes,
+                                     FrameCounters *counters, int grid, cudaStream_t stream);
+cudaError_t launch_wait_bands(const ShardMailbox *mail, uint32_t world, uint32_t epoch, uint32_t *err, cudaStream_t stream);
 cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_route_scatter(const RouteArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_shard_finish(const uint32_t *matrix, uint32_t world, uint32_t rank, uint32_t recv_cap,

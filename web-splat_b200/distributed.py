@@ -60,11 +60,11 @@ class ShardedRenderer:
         L = ws.lib()
         ws._check(L.ws_renderer_shard_configure(self.r._h, self.rank, self.world, int(total_points), pc.num_points(), self.W, self.H))
         self.r._viewport = (self.W, self.H)
-        handles = torch.zeros(256, dtype=torch.uint8)
+        handles = torch.zeros(320, dtype=torch.uint8)
         ws._check(L.ws_renderer_shard_export(self.r._h, C.c_void_p(handles.data_ptr())))
         if self.world > 1:
             dev = torch.device("cuda", torch.cuda.current_device())
-            allh = [torch.zeros(256, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            allh = [torch.zeros(320, dtype=torch.uint8, device=dev) for _ in range(self.world)]
             dist.all_gather(allh, handles.to(dev), group=group)
             allh = torch.cat([h.cpu() for h in allh]).contiguous()
             ws._check(L.ws_renderer_shard_import(self.r._h, C.c_void_p(allh.data_ptr())))
@@ -166,6 +166,18 @@ class ShardedRenderer:
         if self.world > 1:
             dist.all_reduce(self.flag, group=self.group)                 # all bands have landed in the root's frame
         mark("barrier2")
+        if host is not None and self.rank == root:
+            ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), stream))
+
+    def frame_peer(self, args, clear=(0.0, 0.0, 0.0, 0.0), root=0, host=None):
+        """One frame with NO host-side collective at all (ws_renderer_shard_frame_to_root): a single C
+        call per rank; rows, barrier and band arrival are flags in peer-mapped mailboxes."""
+        ws = self.ws
+        L = ws.lib()
+        stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        a = args._c()
+        clr = (C.c_double * 4)(*[float(c) for c in clear])
+        ws._check(L.ws_renderer_shard_frame_to_root(self.r._h, self.pc._h, C.byref(a), root, C.byref(clr), stream))
         if host is not None and self.rank == root:
             ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), stream))
 
