@@ -74,12 +74,13 @@ def run(args):
     clocks = sampler.finish() if sampler else None
 
     # ---- e2e: rank 0 additionally downloads every frame into pinned host memory -------------------
+    copy_stream = torch.cuda.Stream() if rank == 0 else None     # root: download frame f while frame f+1 is produced
     for i in range(Wu):
-        sh.frame_peer(fargs[i % len(fargs)], host=host[i & 1] if rank == 0 else None)
+        sh.frame_peer(fargs[i % len(fargs)], host=host[i & 1] if rank == 0 else None, copy_stream=copy_stream)
     sync_all()
     t0 = time.perf_counter()
     for i in range(K):
-        sh.frame_peer(fargs[(Wu + i) % len(fargs)], host=host[i & 1] if rank == 0 else None)
+        sh.frame_peer(fargs[(Wu + i) % len(fargs)], host=host[i & 1] if rank == 0 else None, copy_stream=copy_stream)
     sync_all()
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)

@@ -235,12 +235,12 @@ WS_API ws_status ws_sort_pairs_u32_host(ws_context *ctx, uint32_t *keys_host, ui
  *   shard_finish    depth sort, binning, tile sort on what this rank received
  *   render_band     stage 3 for the rank's rows; the host layer gathers the bands.
  * Records arrive in global Gaussian-index order, so the result is bit-identical to one GPU.
- * Setup: shard_configure on every rank, exchange the 5x64-byte handles of shard_export (e.g.
+ * Setup: shard_configure on every rank, exchange the 6x64-byte handles of shard_export (e.g.
  * torch.distributed.all_gather), shard_import.  Buffers never move after configure. */
 WS_API ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, uint32_t world, uint64_t total_points,
                                              uint32_t local_points, uint32_t width, uint32_t height);
-WS_API ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_5x64);
-WS_API ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_handles_world_x_5x64);
+WS_API ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_6x64);
+WS_API ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_handles_world_x_6x64);
 WS_API ws_status ws_renderer_shard_begin(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
                                          uint32_t *totals_row_device, void *cuda_stream);
 WS_API ws_status ws_renderer_shard_exchange(ws_renderer *r, const uint32_t *matrix_device, void *cuda_stream);
@@ -256,7 +256,9 @@ WS_API ws_status ws_renderer_shard_frame(const ws_renderer *r, void **device_ptr
 /* The same frame (begin, count rows, exchange, barrier, finish, band -> root, "all bands landed") in ONE
  * call and WITHOUT any host-side collective: the count rows, the barrier and the band-arrival signal are
  * epoch flags the kernels write into the peers' mailboxes (release/acquire at system scope over NVLink).
- * Every rank calls it once per frame; the assembled frame is in rank `root`'s frame buffer. */
+ * Every rank calls it once per frame; the assembled frame is in rank `root`'s frame buffer.  The root keeps
+ * TWO frame buffers (frame parity), so frame f can be downloaded on another stream while frame f+1 is
+ * produced; the root must not start frame f+2 before that download has finished (stream/event ordering). */
 WS_API ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
                                                  uint32_t root, const double clear[4], void *cuda_stream);
 WS_API ws_status ws_renderer_shard_download(ws_renderer *r, void *dst_rgba_host, void *cuda_stream);

@@ -290,8 +290,8 @@ struct ShardState {
     uint32_t *d_route = nullptr; size_t route_words = 0;
     uint32_t *part_band_counts = nullptr, *part_band_bases = nullptr, *hist_dummy = nullptr;
     uint32_t *peer_splats[8] = {}, *peer_keys[8] = {}; uint2 *peer_rects[8] = {};
-    uint8_t *peer_frame[8] = {};               // every rank's assembled-frame buffer (only the root's is written)
-    uint8_t *d_shard_frame = nullptr; size_t shard_frame_bytes = 0;
+    uint8_t *peer_frame[8][2] = {};            // every rank's two assembled-frame buffers (frame parity; only the root's are written)
+    uint8_t *d_shard_frame[2] = {nullptr, nullptr}; size_t shard_frame_bytes = 0;
     ShardMailbox *d_mail = nullptr, *peer_mail[8] = {};   // rows / barrier / band flags written by the peers
     uint32_t epoch = 0;
     uint32_t *pending_signal = nullptr;        // set for the next band composite only
@@ -624,11 +624,11 @@ static void free_shard(ws_renderer *r)
     for (int p = 0; p < 8; p++) {
         if (s.opened[p]) {
             cudaIpcCloseMemHandle(s.peer_splats[p]); cudaIpcCloseMemHandle(s.peer_keys[p]); cudaIpcCloseMemHandle(s.peer_rects[p]);
-            cudaIpcCloseMemHandle(s.peer_frame[p]); cudaIpcCloseMemHandle(s.peer_mail[p]);
+            cudaIpcCloseMemHandle(s.peer_frame[p][0]); cudaIpcCloseMemHandle(s.peer_frame[p][1]); cudaIpcCloseMemHandle(s.peer_mail[p]);
             s.opened[p] = false;
         }
     }
-    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame); cudaFree(s.d_mail);
+    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame[0]); cudaFree(s.d_shard_frame[1]); cudaFree(s.d_mail);
     s = ShardState();
 }
 
@@ -656,23 +656,25 @@ extern "C" ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, 
     CU(cudaMalloc(&s.d_route, s.route_words * 4));
     s.part_band_counts = s.d_route; s.part_band_bases = s.d_route + parts * world; s.hist_dummy = s.d_route + parts * world * 2;
     s.shard_frame_bytes = (size_t)width * height * (r->format == WS_FORMAT_RGBA8_UNORM ? 4 : (r->format == WS_FORMAT_RGBA16_FLOAT ? 8 : 16));
-    CU(cudaMalloc(&s.d_shard_frame, s.shard_frame_bytes));
+    CU(cudaMalloc(&s.d_shard_frame[0], s.shard_frame_bytes)); CU(cudaMalloc(&s.d_shard_frame[1], s.shard_frame_bytes));
     CU(cudaMalloc(&s.d_mail, sizeof(ShardMailbox)));
     CU(cudaMemset(s.d_mail, 0, sizeof(ShardMailbox)));
-    s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects; s.peer_frame[rank] = s.d_shard_frame;
+    s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects;
+    s.peer_frame[rank][0] = s.d_shard_frame[0]; s.peer_frame[rank][1] = s.d_shard_frame[1];
     s.peer_mail[rank] = s.d_mail;
     return WS_OK;
 }
 
-extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_5x64)
+extern "C" ws_status ws_renderer_shard_export(ws_renderer *r, void *handles_6x64)
 {
-    void *handles_3x64 = handles_5x64;
+    void *handles_3x64 = handles_6x64;
     if (!r || !handles_3x64) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (r->shard.world < 1 || !r->d_splats) return fail(WS_ERR_INVALID_ARGUMENT, "call ws_renderer_shard_configure first");
     CU(cudaSetDevice(r->ctx->device));
-    cudaIpcMemHandle_t h[5];
+    cudaIpcMemHandle_t h[6];
     CU(cudaIpcGetMemHandle(&h[0], r->d_splats)); CU(cudaIpcGetMemHandle(&h[1], r->d_keys[0])); CU(cudaIpcGetMemHandle(&h[2], r->d_rects));
-    CU(cudaIpcGetMemHandle(&h[3], r->shard.d_shard_frame)); CU(cudaIpcGetMemHandle(&h[4], r->shard.d_mail));
+    CU(cudaIpcGetMemHandle(&h[3], r->shard.d_shard_frame[0])); CU(cudaIpcGetMemHandle(&h[4], r->shard.d_shard_frame[1]));
+    CU(cudaIpcGetMemHandle(&h[5], r->shard.d_mail));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(handles_3x64, h, sizeof h);
     return WS_OK;
@@ -687,15 +689,16 @@ extern "C" ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_ha
     const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
     for (uint32_t p = 0; p < s.world; p++) {
         if (p == s.rank || s.opened[p]) continue;
-        void *a = nullptr, *b = nullptr, *c = nullptr, *f = nullptr, *m = nullptr;
-        CU(cudaIpcOpenMemHandle(&a, h[p * 5 + 0], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&b, h[p * 5 + 1], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&c, h[p * 5 + 2], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&f, h[p * 5 + 3], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&m, h[p * 5 + 4], cudaIpcMemLazyEnablePeerAccess));
+        void *a = nullptr, *b = nullptr, *c = nullptr, *f = nullptr, *f1 = nullptr, *m = nullptr;
+        CU(cudaIpcOpenMemHandle(&a, h[p * 6 + 0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&b, h[p * 6 + 1], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&c, h[p * 6 + 2], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&f, h[p * 6 + 3], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&f1, h[p * 6 + 4], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&m, h[p * 6 + 5], cudaIpcMemLazyEnablePeerAccess));
         s.peer_mail[p] = static_cast<ShardMailbox *>(m);
         s.peer_splats[p] = static_cast<uint32_t *>(a); s.peer_keys[p] = static_cast<uint32_t *>(b); s.peer_rects[p] = static_cast<uint2 *>(c);
-        s.peer_frame[p] = static_cast<uint8_t *>(f);
+        s.peer_frame[p][0] = static_cast<uint8_t *>(f); s.peer_frame[p][1] = static_cast<uint8_t *>(f1);
         s.opened[p] = true;
     }
     s.imported = true;
@@ -835,7 +838,7 @@ extern "C" ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointclo
     const uint32_t rows = s.band_y0[s.rank + 1] - s.band_y0[s.rank];
     if (rows > 0 && first < s.height) {
         s.pending_signal = &s.peer_mail[root]->flag_band[s.rank];
-        st = render_rows(r, pc, s.peer_frame[root] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], rows);
+        st = render_rows(r, pc, s.peer_frame[root][s.epoch & 1u] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], rows);
         if (st != WS_OK) return st;
     } else {
         return fail(WS_ERR_UNSUPPORTED, "a rank without tile rows (more ranks than tile rows) is not supported");
@@ -883,23 +886,23 @@ extern "C" ws_status ws_renderer_render_band_to_root(ws_renderer *r, ws_pointclo
 {
     if (!r || r->shard.world < 1 || root >= r->shard.world) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding / bad root");
     const ShardState &s = r->shard;
-    if (!s.peer_frame[root]) return fail(WS_ERR_INVALID_ARGUMENT, "peer handles not imported");
+    if (!s.peer_frame[root][0]) return fail(WS_ERR_INVALID_ARGUMENT, "peer handles not imported");
     const size_t pitch = s.shard_frame_bytes / s.height;
     const uint32_t first = s.band_y0[s.rank] * TILE;
     if (first >= s.height) { r->rendered = true; return WS_OK; }
-    return render_rows(r, pc, s.peer_frame[root] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], s.band_y0[s.rank + 1] - s.band_y0[s.rank]);
+    return render_rows(r, pc, s.peer_frame[root][s.epoch & 1u] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], s.band_y0[s.rank + 1] - s.band_y0[s.rank]);
 }
 extern "C" ws_status ws_renderer_shard_frame(const ws_renderer *r, void **device_ptr, size_t *row_pitch_bytes)
 {
     if (!r || !device_ptr || !row_pitch_bytes || r->shard.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
-    *device_ptr = r->shard.d_shard_frame; *row_pitch_bytes = r->shard.shard_frame_bytes / r->shard.height;
+    *device_ptr = r->shard.d_shard_frame[r->shard.epoch & 1u]; *row_pitch_bytes = r->shard.shard_frame_bytes / r->shard.height;
     return WS_OK;
 }
 extern "C" ws_status ws_renderer_shard_download(ws_renderer *r, void *dst_host, void *cuda_stream)
 {
     if (!r || !dst_host || r->shard.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is not configured for sharding");
     CU(cudaSetDevice(r->ctx->device));
-    CU(cudaMemcpyAsync(dst_host, r->shard.d_shard_frame, r->shard.shard_frame_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+    CU(cudaMemcpyAsync(dst_host, r->shard.d_shard_frame[r->shard.epoch & 1u], r->shard.shard_frame_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
     return WS_OK;
 }
 

@@ -128,12 +128,14 @@ route_scan_kernel(RouteArgs a)
     }
 }
 
-// ---- pass 3: routing + compaction + transfer, fused: store records into the owners' buffers
+// ---- pass 3: routing + compaction + transfer, fused: store records into the owners' buffers.
+// Each WARP owns 128 consecutive slots of the partition and moves its own records: one block barrier per
+// partition (to turn the per-warp, per-band counts into offsets) instead of three per band.
 __global__ void __launch_bounds__(RT_THREADS)
 route_scatter_kernel(RouteArgs a)
 {
-    __shared__ uint32_t s_list[RT_PART];         // local slots bound for the current band, in slot order
-    __shared__ uint32_t s_wcnt[RT_WARPS];
+    __shared__ uint32_t s_list[RT_WARPS][32 * RT_SPT];   // per warp: local slots bound for the current band, in slot order
+    __shared__ uint32_t s_wb[RT_WARPS][8];               // per warp and band: number of records
     __shared__ uint32_t s_recv_off[8];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
@@ -154,51 +156,60 @@ route_scatter_kernel(RouteArgs a)
         const uint32_t first = part * RT_PART + tid * RT_SPT;
         uint2 rc[RT_SPT];
         load_rects4(a, first, V, rc);
+        // per-warp counts for every band
+        for (uint32_t d = 0; d < a.world; d++) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < RT_SPT; j++) c += touches_band(rc[j], a.band_y0[d], a.band_y0[d + 1]) ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) s_wb[warp][d] = c;
+        }
+        __syncthreads();
         for (uint32_t d = 0; d < a.world; d++) {
             const uint32_t b0 = a.band_y0[d], b1 = a.band_y0[d + 1];
+            uint32_t wbase = 0;
+            for (uint32_t w = 0; w < warp; w++) wbase += s_wb[w][d];
+            const uint32_t cnt = s_wb[warp][d];
+            if (cnt == 0u) continue;                                           // warp-uniform
             bool go[RT_SPT];
             uint32_t mine = 0;
 #pragma unroll
             for (int j = 0; j < RT_SPT; j++) { go[j] = touches_band(rc[j], b0, b1); mine += go[j] ? 1u : 0u; }
-            // block exclusive scan of `mine` (slot order = thread order, then j)
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if ((int)lane >= o) incl += t;
             }
-            if (lane == 31) s_wcnt[warp] = incl;
-            __syncthreads();
-            uint32_t woff = 0, cnt = 0;
+            uint32_t pos = incl - mine;
+            uint32_t *lst = s_list[warp];
 #pragma unroll
-            for (int w = 0; w < RT_WARPS; w++) { const uint32_t c = s_wcnt[w]; if (w < (int)warp) woff += c; cnt += c; }
-            uint32_t pos = woff + incl - mine;
-#pragma unroll
-            for (int j = 0; j < RT_SPT; j++) if (go[j]) s_list[pos++] = first + j;
-            __syncthreads();
-            const uint32_t dst0 = s_recv_off[d] + a.part_band_bases[(size_t)part * a.world + d];
+            for (int j = 0; j < RT_SPT; j++) if (go[j]) lst[pos++] = first + j;
+            __syncwarp();
+            const uint32_t dst0 = s_recv_off[d] + a.part_band_bases[(size_t)part * a.world + d] + wbase;
             if (dst0 + cnt > a.recv_cap) {
-                if (tid == 0 && cnt) atomicOr(a.err, 2u);                       // receiver capacity exceeded: nothing is written
-            } else if (cnt) {
+                if (lane == 0) atomicOr(a.err, 2u);                             // receiver capacity exceeded: nothing is written
+            } else {
                 uint32_t *ds = a.peer_splats[d] + (size_t)dst0 * 5u;
                 const uint32_t nw = cnt * 5u;
-                uint32_t i = tid;
-                for (; i + 3u * RT_THREADS < nw; i += 4u * RT_THREADS) {      // four independent gathers in flight per thread
+                uint32_t i = lane;
+                for (; i + 96u < nw; i += 128u) {                               // four independent gathers in flight per lane
                     uint32_t v[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const uint32_t ii = i + (uint32_t)u * RT_THREADS, e = ii / 5u, k = ii - e * 5u;
-                        v[u] = a.l_splats[(size_t)s_list[e] * 5u + k];
+                        const uint32_t ii = i + (uint32_t)u * 32u, e = ii / 5u, k = ii - e * 5u;
+                        v[u] = a.l_splats[(size_t)lst[e] * 5u + k];
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) ds[i + (uint32_t)u * RT_THREADS] = v[u];
+                    for (int u = 0; u < 4; u++) ds[i + (uint32_t)u * 32u] = v[u];
                 }
-                for (; i < nw; i += RT_THREADS) {
+                for (; i < nw; i += 32u) {
                     const uint32_t e = i / 5u, k = i - e * 5u;
-                    ds[i] = a.l_splats[(size_t)s_list[e] * 5u + k];
+                    ds[i] = a.l_splats[(size_t)lst[e] * 5u + k];
                 }
-                for (uint32_t e = tid; e < cnt; e += RT_THREADS) {
-                    const uint32_t src = s_list[e];
+                for (uint32_t e = lane; e < cnt; e += 32u) {
+                    const uint32_t src = lst[e];
                     a.peer_keys[d][dst0 + e] = a.l_keys[src];
                     const uint2 r = a.l_rects[src];                            // clip the rectangle to the band's tile rows
                     const uint32_t y0 = r.x >> 16, h = r.y >> 16;
@@ -207,8 +218,9 @@ route_scatter_kernel(RouteArgs a)
                     a.peer_rects[d][dst0 + e] = make_uint2((r.x & 0xffffu) | (ny0 << 16), (r.y & 0xffffu) | ((ny1 - ny0) << 16));
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
+        __syncthreads();
     }
     if (a.peer_mail[a.rank]) {
         // the last CTA to finish tells every rank that this rank's records have landed

@@ -60,11 +60,11 @@ class ShardedRenderer:
         L = ws.lib()
         ws._check(L.ws_renderer_shard_configure(self.r._h, self.rank, self.world, int(total_points), pc.num_points(), self.W, self.H))
         self.r._viewport = (self.W, self.H)
-        handles = torch.zeros(320, dtype=torch.uint8)
+        handles = torch.zeros(384, dtype=torch.uint8)
         ws._check(L.ws_renderer_shard_export(self.r._h, C.c_void_p(handles.data_ptr())))
         if self.world > 1:
             dev = torch.device("cuda", torch.cuda.current_device())
-            allh = [torch.zeros(320, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            allh = [torch.zeros(384, dtype=torch.uint8, device=dev) for _ in range(self.world)]
             dist.all_gather(allh, handles.to(dev), group=group)
             allh = torch.cat([h.cpu() for h in allh]).contiguous()
             ws._check(L.ws_renderer_shard_import(self.r._h, C.c_void_p(allh.data_ptr())))
@@ -81,6 +81,8 @@ class ShardedRenderer:
         self.band = torch.zeros((self.max_rows, self.W, 4), dtype=dt, device=dev)
         self.gathered = torch.zeros((self.world, self.max_rows, self.W, 4), dtype=dt, device=dev)
         self.frame_out = torch.zeros((self.H, self.W, 4), dtype=dt, device=dev)
+        self._frames = 1                                         # mirrors the library's epoch (first frame = 1)
+        self._copied = [None, None]
 
     def frame(self, args, clear=(0.0, 0.0, 0.0, 0.0), gather=True, marks=None):
         """Enqueue one frame on torch's current stream; returns the assembled frame (device tensor).
@@ -169,17 +171,34 @@ class ShardedRenderer:
         if host is not None and self.rank == root:
             ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), stream))
 
-    def frame_peer(self, args, clear=(0.0, 0.0, 0.0, 0.0), root=0, host=None):
+    def frame_peer(self, args, clear=(0.0, 0.0, 0.0, 0.0), root=0, host=None, copy_stream=None):
         """One frame with NO host-side collective at all (ws_renderer_shard_frame_to_root): a single C
-        call per rank; rows, barrier and band arrival are flags in peer-mapped mailboxes."""
-        ws = self.ws
+        call per rank; rows, barrier and band arrival are flags in peer-mapped mailboxes.  With `host`
+        (root only) the assembled frame is downloaded; with `copy_stream` the download runs there and
+        overlaps the next frame (the root keeps two frame buffers, alternating per frame)."""
+        ws, torch = self.ws, self.torch
         L = ws.lib()
-        stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        cur = torch.cuda.current_stream()
+        stream = C.c_void_p(cur.cuda_stream)
+        par = self._frames & 1                                   # parity of the frame buffer this frame fills
+        self._frames += 1
+        is_root = self.rank == root
+        if is_root and copy_stream is not None and self._copied[par] is not None:
+            cur.wait_event(self._copied[par])                    # its previous download must be over before peers overwrite it
         a = args._c()
         clr = (C.c_double * 4)(*[float(c) for c in clear])
         ws._check(L.ws_renderer_shard_frame_to_root(self.r._h, self.pc._h, C.byref(a), root, C.byref(clr), stream))
-        if host is not None and self.rank == root:
-            ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), stream))
+        if host is not None and is_root:
+            if copy_stream is None:
+                ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), stream))
+            else:
+                done = torch.cuda.Event()
+                done.record(cur)
+                copy_stream.wait_event(done)
+                ws._check(L.ws_renderer_shard_download(self.r._h, C.c_void_p(host.data_ptr()), C.c_void_p(copy_stream.cuda_stream)))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                self._copied[par] = ev
 
     def download(self, host):
         """root only: asynchronous copy of the assembled frame into `host` (pinned CPU tensor / numpy array)."""
