@@ -194,6 +194,10 @@ WS_API ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *out);
 WS_API ws_status ws_renderer_set_pair_capacity(ws_renderer *r, uint64_t max_pairs);
 /* per-stage CUDA-event timing on/off (default on; costs 8 event records per frame) */
 WS_API ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled);
+/* With timing off, prepare() replays one CUDA graph (2 clears + 14 kernels) per (cloud, viewport,
+ * capacities) instead of 16 launches -- the frame-graph analogue of the reference recording one command
+ * buffer per frame (src/lib.rs:415-500).  Default on; this switch exists for A/B measurements. */
+WS_API ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled);
 
 /* ---- intermediate read-back (parity tests; synchronises) -------------------
  * Copies an intermediate buffer of the LAST prepared frame to host memory. */

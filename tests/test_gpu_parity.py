@@ -281,3 +281,33 @@ def test_compressed_lower_degree_files(ws, orc, ctx, deg):
     cloud = ws.synth.make_cloud_compressed(8000, 22, sh_deg=deg, codebook=256)
     pos, rot = ws.synth.orbit_camera(200.0)
     _check_compressed(ws, orc, ctx, cloud, pos, rot, 320, 200, max_sh_deg=deg)
+
+
+def test_cuda_graph_path_is_identical(ws, orc, ctx):
+    """With timing off prepare() replays a CUDA graph; the frames must equal the direct-launch ones, also
+    after the cloud / viewport changed (graph rebuild) and when frames are enqueued back to back."""
+    import torch
+    r = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA32_FLOAT, 3, False)
+    ref = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA32_FLOAT, 3, False)
+    r.set_timing(False)
+    ref.set_cuda_graphs(False)
+    stream = torch.cuda.Stream()
+    for n, W, H in ((20000, 320, 200), (20000, 320, 200), (35000, 480, 270), (20000, 320, 200)):
+        cloud = ws.synth.make_cloud(n, 50 + n)
+        pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+        fovx, fovy = ws.synth.fov_for_viewport(W, H)
+        outs = []
+        for az in (10.0, 130.0, 250.0):                      # three frames in flight on one stream
+            pos, rot = ws.synth.orbit_camera(az)
+            args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
+            t = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+            r.prepare(stream, pc, args)
+            r.render(t, pc, stream=stream)
+            t2 = torch.empty_like(t)
+            ref.prepare(None, pc, args)
+            ref.render(t2, pc)
+            outs.append((t, t2))
+        torch.cuda.synchronize()
+        for t, t2 in outs:
+            assert torch.equal(t, t2)
+        assert r.stats()["num_pairs"] == ref.stats()["num_pairs"]

@@ -341,6 +341,11 @@ struct ws_renderer {
     cudaStream_t last_stream = nullptr;
     uint32_t last_n = 0;
     ShardState shard;
+    // CUDA graph of one prepare() (clears + 14 kernels), replayed while (cloud, viewport, capacities) stay the same
+    bool use_graphs = true;
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t prep_exec = nullptr;
+    struct { const ws_pointcloud *pc; const void *gaussians, *scratch; uint32_t n, W, H, pair_cap, n_cap; } prep_key = {};
 };
 
 static void free_shard(ws_renderer *r);
@@ -366,6 +371,8 @@ extern "C" void ws_renderer_destroy(ws_renderer *r)
     free_sort_stuff(r);
     cudaFree(r->d_uniforms); cudaFree(r->d_ranges); cudaFree(r->d_frame);
     if (r->ev_ok) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(r->ev[i]);
+    if (r->prep_exec) cudaGraphExecDestroy(r->prep_exec);
+    if (r->cap_stream) cudaStreamDestroy(r->cap_stream);
     delete r;
 }
 
@@ -410,6 +417,12 @@ extern "C" ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled)
 {
     if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
     r->timing = enabled != 0;
+    return WS_OK;
+}
+extern "C" ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled)
+{
+    if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
+    r->use_graphs = enabled != 0;
     return WS_OK;
 }
 
@@ -507,7 +520,8 @@ static ws_status validate_frame(ws_renderer *r, ws_pointcloud *pc, const ws_spla
 }
 
 // uniforms + per-frame clears (everything before stage 1)
-static ws_status begin_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, uint32_t capacity_points, cudaStream_t stream)
+static ws_status begin_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, uint32_t capacity_points, cudaStream_t stream,
+                            bool with_clears = true)
 {
     const uint32_t W = args->viewport[0], H = args->viewport[1];
     const uint32_t tx = (W + TILE - 1) / TILE, ty = (H + TILE - 1) / TILE;
@@ -526,8 +540,10 @@ static ws_status begin_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatti
 
     // pageable source: the runtime stages the 0.5 KB before returning, so h_uniforms may be reused
     CU(cudaMemcpyAsync(r->d_uniforms, &U, sizeof U, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
-    CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)tiles * 8, stream));    // {begin, ~end} identities for atomicMin
+    if (with_clears) {
+        CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
+        CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)tiles * 8, stream));    // {begin, ~end} identities for atomicMin
+    }
     return WS_OK;
 }
 
@@ -587,15 +603,12 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
     return WS_OK;
 }
 
-extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, void *cuda_stream)
+// clears + stage 1 + stage 2 of the plain (single-GPU) frame, on `stream`
+static ws_status enqueue_prepare_body(ws_renderer *r, ws_pointcloud *pc, cudaStream_t stream)
 {
-    ws_status st = validate_frame(r, pc, args);
-    if (st != WS_OK) return st;
-    if (r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is configured for sharding: use ws_renderer_shard_begin/exchange/finish");
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
-    CU(cudaSetDevice(r->ctx->device));
-    st = begin_frame(r, pc, args, pc->n, stream);
-    if (st != WS_OK) return st;
+    const FrameUniforms &U = r->h_uniforms;
+    CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
+    CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)U.tiles_x * U.tiles_y * 8, stream));    // {begin, ~end} identities for atomicMin
     if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
     {   // ---- stage 1
         PreprocessArgs a;
@@ -607,8 +620,45 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
         CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
-    st = enqueue_stage2(r, stream);
+    return enqueue_stage2(r, stream);
+}
+
+extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, void *cuda_stream)
+{
+    ws_status st = validate_frame(r, pc, args);
     if (st != WS_OK) return st;
+    if (r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is configured for sharding: use ws_renderer_shard_begin/exchange/finish");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(r->ctx->device));
+    st = begin_frame(r, pc, args, pc->n, stream, /*with_clears=*/false);     // uniforms only; capacities may (re)allocate
+    if (st != WS_OK) return st;
+    if (r->use_graphs && !r->timing) {
+        // One CUDA graph per (cloud, viewport, capacities): 2 memsets + 14 kernels become one launch.  Every kernel
+        // reads its sizes (N, V, P) from device memory, so the graph is independent of the frame's content.
+        const FrameUniforms &U = r->h_uniforms;
+        auto &k = r->prep_key;
+        const bool same = r->prep_exec && k.pc == pc && k.gaussians == pc->d_gaussians && k.scratch == r->d_scratch && k.n == pc->n &&
+                          k.W == U.width && k.H == U.height && k.pair_cap == r->pair_cap && k.n_cap == r->n_cap;
+        if (!same) {
+            if (r->prep_exec) { cudaGraphExecDestroy(r->prep_exec); r->prep_exec = nullptr; }
+            if (!r->cap_stream) CU(cudaStreamCreateWithFlags(&r->cap_stream, cudaStreamNonBlocking));
+            CU(cudaStreamBeginCapture(r->cap_stream, cudaStreamCaptureModeThreadLocal));
+            st = enqueue_prepare_body(r, pc, r->cap_stream);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(r->cap_stream, &g);
+            if (st != WS_OK) { if (g) cudaGraphDestroy(g); return st; }
+            if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture");
+            e = cudaGraphInstantiate(&r->prep_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { r->prep_exec = nullptr; return fail_cuda(e, "cudaGraphInstantiate"); }
+            k.pc = pc; k.gaussians = pc->d_gaussians; k.scratch = r->d_scratch; k.n = pc->n; k.W = U.width; k.H = U.height;
+            k.pair_cap = r->pair_cap; k.n_cap = r->n_cap;
+        }
+        CU(cudaGraphLaunch(r->prep_exec, stream));
+    } else {
+        st = enqueue_prepare_body(r, pc, stream);
+        if (st != WS_OK) return st;
+    }
     r->prepared = true;
     r->last_stream = stream;
     r->last_n = pc->n;
