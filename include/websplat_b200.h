@@ -94,6 +94,60 @@ typedef struct {
  * replaces PointCloud::new (src/pointcloud.rs:99-199).  Copies the host buffers to
  * HBM (synchronous); the caller keeps ownership of its memory. */
 WS_API ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_desc *desc, ws_pointcloud **out);
+/* .ply ingest: replaces PlyReader::new + read (src/io/ply.rs:28-48,165-195) and
+ * GenericGaussianPointCloud::new (src/io/mod.rs:63-105).  `file_bytes` is the whole .ply file
+ * (header + binary vertex block, little or big endian).  The header is parsed on the host; the
+ * per-vertex conversion (sigmoid, exp, quaternion normalise, build_cov, f16, SH transpose),
+ * the bounding box, centroid and plane normal run on the GPU.  sh_deg comes from the number of
+ * f_* properties (io/ply.rs:102-114); `comment mip=`, `kernel_size=`, `background_color=` fill the
+ * optional metadata (io/ply.rs:121-160).  ascii files -> WS_ERR_UNSUPPORTED like the reference's todo!(). */
+/* Host-only header probe (no CUDA): what PlyReader::new extracts from the header (io/ply.rs:28-48),
+ * with the same failure cases ws_pointcloud_create_from_ply reports. */
+typedef struct {
+    uint64_t num_points;       /* element vertex N, io/ply.rs:116-120 */
+    uint64_t data_offset;      /* first byte after end_header */
+    uint32_t sh_deg;           /* io/ply.rs:102-114 */
+    uint32_t stride_bytes;     /* bytes per vertex */
+    uint32_t big_endian;
+    int32_t has_mip_splatting; int32_t mip_splatting;
+    int32_t has_kernel_size;   float kernel_size;
+    int32_t has_background;    float background_color[3];
+} ws_ply_info;
+WS_API ws_status ws_ply_probe(const void *file_bytes, uint64_t file_len, ws_ply_info *out);
+WS_API ws_status ws_pointcloud_create_from_ply(ws_context *ctx, const void *file_bytes, uint64_t file_len, ws_pointcloud **out);
+/* .npz (compressed 3DGS) ingest: replaces the array post-processing of NpzReader::read
+ * (src/io/npz.rs:58-225) and GenericGaussianPointCloud::new_compressed (src/io/mod.rs:107-150).
+ * The caller decodes the zip/npy container (the reference uses the npyz crate) and passes the arrays by
+ * name as they are stored; the GPU assembles the 24-B GaussianCompressed records, interleaves the i8
+ * SH codebook (dc then rest), dequantises rotation / scaling and builds the f16 covariance codebook
+ * (build_cov, src/utils.rs:194-204), and reduces bbox (from the unit cube) / centroid / plane normal. */
+typedef struct {
+    const void *xyz;                 /* "xyz"              num_points x 3 f16 */
+    const int8_t *opacity;           /* "opacity"          num_points i8 */
+    const int8_t *scaling_factor;    /* "scaling_factor"   num_points i8, or NULL when the file has none */
+    const int32_t *gaussian_indices; /* "gaussian_indices" num_points i32, or NULL (identity) */
+    const int32_t *feature_indices;  /* "feature_indices"  num_points i32, or NULL (identity) */
+    uint64_t num_points;
+    const int8_t *scaling;           /* "scaling"          num_covars x 3 i8 */
+    const int8_t *rotation;          /* "rotation"         num_covars x 4 i8 (w,x,y,z) */
+    uint64_t num_covars;
+    const int8_t *features_dc;       /* "features_dc"      num_features x 3 i8 */
+    const int8_t *features_rest;     /* "features_rest"    num_features x ((sh_deg+1)^2 - 1) x 3 i8 */
+    uint64_t num_features;
+    uint32_t sh_deg;                 /* from features_rest.shape[1] + 1, src/io/npz.rs:33-37 */
+    float scaling_scale;  int32_t scaling_zero_point;     /* src/io/npz.rs:65-68 */
+    float rotation_scale; int32_t rotation_zero_point;    /* src/io/npz.rs:70-73 */
+    ws_quantization4 quantization;   /* features_dc / features_rest / opacity / scaling_factor scale + zero point, src/io/npz.rs:216-221 */
+    int32_t has_mip_splatting; int32_t mip_splatting;
+    int32_t has_kernel_size;   float kernel_size;
+    int32_t has_background;    float background_color[3];
+} ws_c3dgs_arrays;
+WS_API ws_status ws_pointcloud_create_from_c3dgs(ws_context *ctx, const ws_c3dgs_arrays *arrays, ws_pointcloud **out);
+/* test / debug read-back of the resident layouts: which = 0 Gaussian records (28 B, or 24 B
+ * compressed), 1 SH records (96 B raw; i8 codebook compressed), 2 xyz plane (12 B), 3 covariance
+ * codebook (12 B, compressed only).  ws_pointcloud_buffer_bytes gives the size to allocate. */
+WS_API uint64_t ws_pointcloud_buffer_bytes(const ws_pointcloud *pc, int32_t which);
+WS_API ws_status ws_pointcloud_read(const ws_pointcloud *pc, int32_t which, void *dst, uint64_t dst_bytes);
 WS_API void ws_pointcloud_destroy(ws_pointcloud *pc);
 /* getters, src/pointcloud.rs:201-349 */
 WS_API uint32_t ws_pointcloud_num_points(const ws_pointcloud *pc);
@@ -102,6 +156,7 @@ WS_API int32_t ws_pointcloud_compressed(const ws_pointcloud *pc);
 WS_API ws_status ws_pointcloud_bbox(const ws_pointcloud *pc, ws_aabb *out);
 WS_API ws_status ws_pointcloud_center(const ws_pointcloud *pc, float out[3]);
 WS_API int32_t ws_pointcloud_up(const ws_pointcloud *pc, float out[3]);                 /* returns has_up */
+WS_API int32_t ws_pointcloud_background_color(const ws_pointcloud *pc, float out[3]);   /* GenericGaussianPointCloud::background_color, src/io/mod.rs:41; returns 1 if Some */
 WS_API int32_t ws_pointcloud_mip_splatting(const ws_pointcloud *pc, int32_t *out);      /* returns has_value */
 WS_API int32_t ws_pointcloud_dilation_kernel_size(const ws_pointcloud *pc, float *out); /* returns has_value */
 

@@ -66,6 +66,11 @@ def lib():
         L.wso_composite.restype = None
         L.wso_composite.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
         L.wso_tile_rects.restype = None
+        L.wso_ply_convert.restype = C.c_int
+        L.wso_ply_convert.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
+        L.wso_c3dgs_convert.restype = C.c_int
+        L.wso_c3dgs_convert.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32,
+                                        C.c_float, C.c_int32, C.c_float, C.c_int32, vp, vp, vp, vp, vp, vp]
         L.wso_tile_rects.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(C.c_uint64)]
         L.wso_num_threads.restype = C.c_int
         _lib = L
@@ -185,3 +190,44 @@ def render_frame(cloud, pos, rot_wxyz, W, H, fovx, fovy, clear=(0, 0, 0, 0), wan
     img = composite(splats, order, W, H, clear, want_sens)
     return dict(image=img[0] if want_sens else img, sens=img[1] if want_sens else None,
                 splats=splats, keys=keys, order=order, cam=cam, settings=st)
+
+
+def ply_convert(vertices, sh_deg):
+    """vertices: (n, floats_per_vertex) float32 in the 3DGS .ply property order.
+    Returns dict(gaussians (n,28) u8, sh_coefs (n,96) u8, bbox[6], center[3], up or None)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    n, stride = v.shape
+    assert stride == 14 + 3 * (sh_deg + 1) ** 2
+    g = np.zeros((n, 28), np.uint8)
+    sh = np.zeros((n, 96), np.uint8)
+    bbox = np.zeros(6, np.float32); center = np.zeros(3, np.float32); up = np.zeros(3, np.float32)
+    with np.errstate(all="ignore"):
+        has_up = lib().wso_ply_convert(_p(v), n, stride, sh_deg, _p(g), _p(sh), _p(bbox), _p(center), _p(up))
+    return dict(gaussians=g, sh_coefs=sh, bbox=bbox, center=center, up=up if has_up else None)
+
+
+def c3dgs_convert(arrays):
+    """arrays: dict of the .npz members (io/npz.rs:58-160).  Returns gaussians (n,24) u8, sh_coefs i8 (K, 3C),
+    covars (Kc, 12) u8, bbox[6], center[3], up or None."""
+    def opt(name, dt):
+        return np.ascontiguousarray(arrays[name], dtype=dt) if arrays.get(name) is not None else None
+    xyz = np.ascontiguousarray(arrays["xyz"], dtype=np.float16).reshape(-1, 3)
+    n = len(xyz)
+    opacity = np.ascontiguousarray(arrays["opacity"], np.int8).reshape(-1)
+    sf, gi, fi = opt("scaling_factor", np.int8), opt("gaussian_indices", np.int32), opt("feature_indices", np.int32)
+    scaling = np.ascontiguousarray(arrays["scaling"], np.int8).reshape(-1, 3)
+    rotation = np.ascontiguousarray(arrays["rotation"], np.int8).reshape(-1, 4)
+    dc = np.ascontiguousarray(arrays["features_dc"], np.int8).reshape(-1, 3)
+    rest = np.ascontiguousarray(arrays["features_rest"], np.int8)
+    sh_deg = int(round((rest.shape[1] + 1) ** 0.5)) - 1 if rest.ndim == 3 else 0
+    per = 3 * (sh_deg + 1) ** 2
+    g = np.zeros((n, 24), np.uint8); sh = np.zeros((len(dc), per), np.int8); cov = np.zeros((len(scaling), 12), np.uint8)
+    bbox = np.zeros(6, np.float32); center = np.zeros(3, np.float32); up = np.zeros(3, np.float32)
+    pn = lambda a: _p(a) if a is not None else None
+    with np.errstate(all="ignore"):
+        has_up = lib().wso_c3dgs_convert(_p(xyz.view(np.uint16)), _p(opacity), pn(sf), pn(gi), pn(fi), n, _p(scaling), _p(rotation), len(scaling),
+                                         _p(dc), _p(rest), len(dc), sh_deg,
+                                         float(arrays.get("scaling_scale", 1.0)), int(arrays.get("scaling_zero_point", 0)),
+                                         float(arrays.get("rotation_scale", 1.0)), int(arrays.get("rotation_zero_point", 0)),
+                                         _p(g), _p(sh), _p(cov), _p(bbox), _p(center), _p(up))
+    return dict(gaussians=g, sh_coefs=sh, covars=cov, sh_deg=sh_deg, bbox=bbox, center=center, up=up if has_up else None)

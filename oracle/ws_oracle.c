@@ -716,6 +716,170 @@ WSO_API void wso_tile_rects(const uint16_t *splats, uint32_t V, uint32_t W, uint
     if (total_pairs) *total_pairs = tot;
 }
 
+/* ------------------------------------------------------------------------------------
+ * .ply vertex conversion -- PlyReader::read_line, io/ply.rs:50-100, with
+ * sigmoid (utils.rs:206-212), build_cov (utils.rs:194-203) and cgmath 0.18 (git dependency, absent from
+ * /root/reference; restated from its published source): Quaternion::normalize = q * (1/|q|),
+ * Matrix3::from(Quaternion) with the x2/y2/z2 doubling form, column-major Matrix3 products.
+ * `vertices` is the file's binary vertex block, already in host byte order, `stride_floats` floats per
+ * vertex in the fixed order x y z nx ny nz f_dc[3] f_rest[3][C-1] opacity scale[3] rot[4].
+ * Outputs: n x 28 B Gaussian records, n x 96 B [[f16;3];16] SH.  Also the GenericGaussianPointCloud::new
+ * statistics (io/mod.rs:63-105,185-284) exactly as the reference computes them -- f32, file order:
+ * bbox[6] (grown from the zero box), center[3], up[3]; returns 1 when `up` is Some. */
+static float wso_sigmoid(float x)
+{
+    if (x >= 0.f) return 1.f / (1.f + expf(-x));
+    float e = expf(x);
+    return e / (1.f + e);
+}
+
+/* Quaternion::normalize then build_cov (utils.rs:194-203).  cgmath 0.18: InnerSpace::normalize = self * (1 / magnitude),
+ * Quaternion dot = s*s + v.dot(v), Vector3 dot = (x*x + y*y) + z*z, Matrix3::from(Quaternion) in the doubling form. */
+static void wso_build_cov(float qw, float qx, float qy, float qz, const float sc[3], float out[6])
+{
+    float mag = sqrtf(qw * qw + (qx * qx + qy * qy + qz * qz));
+    float inv = 1.f / mag;
+    qw = qw * inv; qx = qx * inv; qy = qy * inv; qz = qz * inv;
+    float x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    float xx2 = x2 * qx, xy2 = x2 * qy, xz2 = x2 * qz, yy2 = y2 * qy, yz2 = y2 * qz, zz2 = z2 * qz;
+    float sy2 = y2 * qw, sz2 = z2 * qw, sx2 = x2 * qw;
+    float R[3][3] = {{1.f - yy2 - zz2, xy2 + sz2, xz2 - sy2},
+                     {xy2 - sz2, 1.f - xx2 - zz2, yz2 + sx2},
+                     {xz2 + sy2, yz2 - sx2, 1.f - xx2 - yy2}};   /* R[column][row] */
+    float L[3][3], M[3][3];
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) L[c][r] = R[c][r] * sc[c];   /* r * diag(s) */
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) { float m = L[0][r] * L[0][c]; m = m + L[1][r] * L[1][c]; m = m + L[2][r] * L[2][c]; M[c][r] = m; }
+    out[0] = M[0][0]; out[1] = M[0][1]; out[2] = M[0][2]; out[3] = M[1][1]; out[4] = M[1][2]; out[5] = M[2][2];
+}
+
+/* GenericGaussianPointCloud::new / new_compressed statistics (io/mod.rs:74-89,119-134,185-284), f32 in file order.
+ * xyz: n points, `stride` floats apart; box0 = 0 (Aabb::zeroed) or 1 (Aabb::unit). */
+static int wso_cloud_stats(const float *xyz, uint32_t n, uint32_t stride, float box0, float bbox[6], float center[3], float up[3])
+{
+    for (int d = 0; d < 3; d++) { bbox[d] = -box0; bbox[3 + d] = box0; }
+    float sum[3] = {0.f, 0.f, 0.f};
+    for (uint32_t i = 0; i < n; i++) {
+        const float *v = xyz + (size_t)i * stride;
+        for (int d = 0; d < 3; d++) {
+            bbox[d] = fminf(bbox[d], v[d]); bbox[3 + d] = fmaxf(bbox[3 + d], v[d]);
+            sum[d] = sum[d] + v[d];
+        }
+    }
+    float rn = 1.0f / (float)n;
+    for (int d = 0; d < 3; d++) center[d] = sum[d] * rn;
+    up[0] = up[1] = up[2] = 0.f;
+    int has_up = 0;
+    if (n >= 3) {
+        float xx = 0.f, xy = 0.f, xz = 0.f, yy = 0.f, yz = 0.f, zz = 0.f;
+        for (uint32_t i = 0; i < n; i++) {
+            const float *v = xyz + (size_t)i * stride;
+            float rx = v[0] - center[0], ry = v[1] - center[1], rz = v[2] - center[2];
+            xx += rx * rx; xy += rx * ry; xz += rx * rz; yy += ry * ry; yz += ry * rz; zz += rz * rz;
+        }
+        float fn = (float)n;
+        xx /= fn; xy /= fn; xz /= fn; yy /= fn; yz /= fn; zz /= fn;
+        float w[3] = {0.f, 0.f, 0.f};
+        float det[3] = {yy * zz - yz * yz, xx * zz - xz * xz, xx * yy - xy * xy};
+        float ax[3][3] = {{det[0], xz * yz - xy * zz, xy * yz - xz * yy},
+                          {xz * yz - xy * zz, det[1], xy * xz - yz * xx},
+                          {xy * yz - xz * yy, xy * xz - yz * xx, det[2]}};
+        for (int k = 0; k < 3; k++) {
+            float weight = det[k] * det[k];
+            if (w[0] * ax[k][0] + w[1] * ax[k][1] + w[2] * ax[k][2] < 0.f) weight = -weight;
+            for (int d = 0; d < 3; d++) w[d] += ax[k][d] * weight;
+        }
+        float m = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        float rm = 1.f / m;
+        float nr[3] = {w[0] * rm, w[1] * rm, w[2] * rm};
+        if (nr[1] < 0.f) { nr[0] = -nr[0]; nr[1] = -nr[1]; nr[2] = -nr[2]; }
+        if (isfinite(nr[0]) && isfinite(nr[1]) && isfinite(nr[2])) { has_up = 1; up[0] = nr[0]; up[1] = nr[1]; up[2] = nr[2]; }
+    }
+    {
+        float dx = bbox[3] - bbox[0], dy = bbox[4] - bbox[1], dz = bbox[5] - bbox[2];
+        if (sqrtf(dx * dx + dy * dy + dz * dz) / 2.f < 10.f) has_up = 0;
+    }
+    return has_up;
+}
+
+WSO_API int wso_ply_convert(const float *vertices, uint32_t n, uint32_t stride_floats, uint32_t sh_deg,
+                            uint8_t *gaussians, uint8_t *sh_coefs, float bbox[6], float center[3], float up[3])
+{
+    const uint32_t ncoef = (sh_deg + 1u) * (sh_deg + 1u);
+#pragma omp parallel for schedule(static)
+    for (int64_t ii = 0; ii < (int64_t)n; ii++) {
+        const uint32_t i = (uint32_t)ii;
+        const float *v = vertices + (size_t)i * stride_floats;
+        uint16_t sh[48];
+        memset(sh, 0, sizeof sh);
+        for (int ch = 0; ch < 3; ch++) sh[ch] = wso_f32_to_f16(v[6 + ch]);
+        for (uint32_t c = 0; c + 1u < ncoef; c++)
+            for (uint32_t ch = 0; ch < 3u; ch++) sh[(c + 1u) * 3u + ch] = wso_f32_to_f16(v[9u + ch * (ncoef - 1u) + c]);
+        const float *t = v + 9u + (ncoef - 1u) * 3u;
+        float opacity = wso_sigmoid(t[0]);
+        float sc[3] = {expf(t[1]), expf(t[2]), expf(t[3])};
+        float M6[6];
+        wso_build_cov(t[4], t[5], t[6], t[7], sc, M6);
+        uint8_t *g = gaussians + (size_t)i * 28u;
+        memcpy(g, v, 12);
+        uint16_t h[8] = {wso_f32_to_f16(opacity), 0, wso_f32_to_f16(M6[0]), wso_f32_to_f16(M6[1]), wso_f32_to_f16(M6[2]),
+                         wso_f32_to_f16(M6[3]), wso_f32_to_f16(M6[4]), wso_f32_to_f16(M6[5])};
+        memcpy(g + 12, h, 16);
+        memcpy(sh_coefs + (size_t)i * 96u, sh, 96);
+    }
+    return wso_cloud_stats(vertices, n, stride_floats, 0.f, bbox, center, up);
+}
+
+/* .npz array post-processing -- NpzReader::read, io/npz.rs:58-225.
+ * Inputs are the stored arrays; scaling_factor / gaussian_indices / feature_indices may be NULL.
+ * Outputs: n x 24 B GaussianCompressed, num_features x 3C i8 SH codebook (dc then rest),
+ * num_covars x 12 B f16 covariance codebook, and the new_compressed statistics. */
+WSO_API int wso_c3dgs_convert(const uint16_t *xyz_f16, const int8_t *opacity, const int8_t *scaling_factor,
+                              const int32_t *gaussian_indices, const int32_t *feature_indices, uint32_t n,
+                              const int8_t *scaling, const int8_t *rotation, uint32_t num_covars,
+                              const int8_t *features_dc, const int8_t *features_rest, uint32_t num_features, uint32_t sh_deg,
+                              float scaling_scale, int32_t scaling_zero_point, float rotation_scale, int32_t rotation_zero_point,
+                              uint8_t *gaussians, int8_t *sh_out, uint8_t *covars, float bbox[6], float center[3], float up[3])
+{
+    const uint32_t per = (sh_deg + 1u) * (sh_deg + 1u) * 3u, rest = per - 3u;
+    float *xyz = (float *)malloc((size_t)(n ? n : 1) * 12u);
+    for (uint32_t i = 0; i < n; i++) {
+        uint8_t *g = gaussians + (size_t)i * 24u;
+        for (int d = 0; d < 3; d++) xyz[(size_t)i * 3u + d] = wso_f16_to_f32(xyz_f16[(size_t)i * 3u + d]);
+        memcpy(g, xyz + (size_t)i * 3u, 12);
+        g[12] = (uint8_t)opacity[i];
+        g[13] = scaling_factor ? (uint8_t)scaling_factor[i] : 0;
+        g[14] = g[15] = 0;
+        uint32_t gi = gaussian_indices ? (uint32_t)gaussian_indices[i] : i, fi = feature_indices ? (uint32_t)feature_indices[i] : i;
+        memcpy(g + 16, &gi, 4); memcpy(g + 20, &fi, 4);
+    }
+    for (uint32_t e = 0; e < num_features; e++) {
+        int8_t *o = sh_out + (size_t)e * per;
+        o[0] = features_dc[(size_t)e * 3u]; o[1] = features_dc[(size_t)e * 3u + 1]; o[2] = features_dc[(size_t)e * 3u + 2];
+        for (uint32_t j = 0; j < rest; j++) o[3u + j] = features_rest[(size_t)e * rest + j];
+    }
+    const float szp = (float)scaling_zero_point, rzp = (float)rotation_zero_point;
+    for (uint32_t i = 0; i < num_covars; i++) {
+        float s[3], q[4], M6[6];
+        for (int d = 0; d < 3; d++) {
+            float v = ((float)scaling[(size_t)i * 3u + d] - szp) * scaling_scale;
+            s[d] = scaling_factor ? fmaxf(v, 0.f) : expf(v);
+        }
+        if (scaling_factor) {
+            float inv = 1.f / sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+            s[0] = s[0] * inv; s[1] = s[1] * inv; s[2] = s[2] * inv;
+        }
+        for (int d = 0; d < 4; d++) q[d] = ((float)rotation[(size_t)i * 4u + d] - rzp) * rotation_scale;
+        wso_build_cov(q[0], q[1], q[2], q[3], s, M6);
+        uint16_t h[6];
+        for (int d = 0; d < 6; d++) h[d] = wso_f32_to_f16(M6[d]);
+        memcpy(covars + (size_t)i * 12u, h, 12);
+    }
+    int has_up = wso_cloud_stats(xyz, n, 3, 1.f, bbox, center, up);
+    free(xyz);
+    return has_up;
+}
+
 WSO_API int wso_num_threads(void)
 {
 #ifdef _OPENMP

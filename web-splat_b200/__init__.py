@@ -84,6 +84,23 @@ class ws_pointcloud_desc(C.Structure):
     ]
 
 
+class ws_c3dgs_arrays(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("opacity", C.c_void_p), ("scaling_factor", C.c_void_p), ("gaussian_indices", C.c_void_p),
+                ("feature_indices", C.c_void_p), ("num_points", C.c_uint64), ("scaling", C.c_void_p), ("rotation", C.c_void_p),
+                ("num_covars", C.c_uint64), ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("num_features", C.c_uint64),
+                ("sh_deg", C.c_uint32), ("scaling_scale", C.c_float), ("scaling_zero_point", C.c_int32),
+                ("rotation_scale", C.c_float), ("rotation_zero_point", C.c_int32), ("quantization", ws_quantization4),
+                ("has_mip_splatting", C.c_int32), ("mip_splatting", C.c_int32), ("has_kernel_size", C.c_int32),
+                ("kernel_size", C.c_float), ("has_background", C.c_int32), ("background_color", C.c_float * 3)]
+
+
+class ws_ply_info(C.Structure):
+    _fields_ = [("num_points", C.c_uint64), ("data_offset", C.c_uint64), ("sh_deg", C.c_uint32), ("stride_bytes", C.c_uint32),
+                ("big_endian", C.c_uint32), ("has_mip_splatting", C.c_int32), ("mip_splatting", C.c_int32),
+                ("has_kernel_size", C.c_int32), ("kernel_size", C.c_float), ("has_background", C.c_int32),
+                ("background_color", C.c_float * 3)]
+
+
 class ws_splatting_args(C.Structure):
     _fields_ = [
         ("cam_position", C.c_float * 3), ("cam_rotation_wxyz", C.c_float * 4),
@@ -113,7 +130,9 @@ class ws_frame_stats(C.Structure):
 # every symbol include/websplat_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "ws_status_string", "ws_last_error", "ws_context_create", "ws_context_destroy", "ws_context_device",
-    "ws_context_sm_count", "ws_pointcloud_create", "ws_pointcloud_destroy", "ws_pointcloud_num_points",
+    "ws_context_sm_count", "ws_pointcloud_create", "ws_pointcloud_create_from_ply", "ws_pointcloud_create_from_c3dgs", "ws_pointcloud_read",
+    "ws_pointcloud_buffer_bytes", "ws_ply_probe",
+    "ws_pointcloud_background_color", "ws_pointcloud_destroy", "ws_pointcloud_num_points",
     "ws_pointcloud_sh_deg", "ws_pointcloud_compressed", "ws_pointcloud_bbox", "ws_pointcloud_center",
     "ws_pointcloud_up", "ws_pointcloud_mip_splatting", "ws_pointcloud_dilation_kernel_size",
     "ws_aabb_center", "ws_aabb_radius", "ws_camera_fit_near_far", "ws_renderer_create", "ws_renderer_destroy",
@@ -157,6 +176,11 @@ def lib():
         "ws_context_device": (C.c_int, [vp]),
         "ws_context_sm_count": (C.c_int, [vp]),
         "ws_pointcloud_create": (i32, [vp, C.POINTER(ws_pointcloud_desc), C.POINTER(vp)]),
+        "ws_pointcloud_create_from_ply": (i32, [vp, vp, u64, C.POINTER(vp)]),
+        "ws_pointcloud_create_from_c3dgs": (i32, [vp, C.POINTER(ws_c3dgs_arrays), C.POINTER(vp)]),
+        "ws_pointcloud_buffer_bytes": (u64, [vp, i32]),
+        "ws_pointcloud_read": (i32, [vp, i32, vp, u64]),
+        "ws_ply_probe": (i32, [vp, u64, C.POINTER(ws_ply_info)]),
         "ws_pointcloud_destroy": (None, [vp]),
         "ws_pointcloud_num_points": (u32, [vp]),
         "ws_pointcloud_sh_deg": (u32, [vp]),
@@ -164,6 +188,7 @@ def lib():
         "ws_pointcloud_bbox": (i32, [vp, C.POINTER(ws_aabb)]),
         "ws_pointcloud_center": (i32, [vp, C.POINTER(f32 * 3)]),
         "ws_pointcloud_up": (i32, [vp, C.POINTER(f32 * 3)]),
+        "ws_pointcloud_background_color": (i32, [vp, C.POINTER(f32 * 3)]),
         "ws_pointcloud_mip_splatting": (i32, [vp, C.POINTER(i32)]),
         "ws_pointcloud_dilation_kernel_size": (i32, [vp, C.POINTER(f32)]),
         "ws_aabb_center": (None, [C.POINTER(ws_aabb), C.POINTER(f32 * 3)]),
@@ -400,6 +425,119 @@ class PointCloud:
         _check(lib().ws_pointcloud_create(ctx._h, C.byref(d), C.byref(self._h)))
         return self
 
+    @classmethod
+    def from_ply(cls, ctx, file):
+        """io/mod.rs:44-61 (`GenericGaussianPointCloud::load`) + PointCloud::new for a .ply: `file` is a
+        path, a bytes-like object or a file object.  The vertex block is converted on the GPU."""
+        if hasattr(file, "read"):
+            data = file.read()
+        elif isinstance(file, (bytes, bytearray, memoryview)):
+            data = bytes(file)
+        else:
+            with open(file, "rb") as f:
+                data = f.read()
+        self = object.__new__(cls)
+        self._h = C.c_void_p()
+        self._ctx = ctx
+        buf = np.frombuffer(data, dtype=np.uint8)
+        _check(lib().ws_pointcloud_create_from_ply(ctx._h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(self._h)))
+        return self
+
+    @classmethod
+    def from_npz(cls, ctx, file):
+        """io/mod.rs:53-58 + NpzReader (io/npz.rs:29-225) + PointCloud::new for a compressed .npz: `file` is a path,
+        a file object, bytes, or a dict of the already-decoded members.  numpy decodes the zip/npy container;
+        the arrays are assembled into the GPU layouts on the device."""
+        if isinstance(file, dict):
+            a = file
+        else:
+            if isinstance(file, (bytes, bytearray, memoryview)):
+                import io
+                file = io.BytesIO(bytes(file))
+            with np.load(file) as z:
+                a = {k: z[k] for k in z.files}
+        keep = []
+
+        def arr(name, dt, required=True):
+            if a.get(name) is None:
+                if required:
+                    raise WsError(-1, "websplat_b200: invalid argument (status -1): array %r missing" % name)   # io/npz.rs:265-275
+                return None
+            v = np.ascontiguousarray(a[name], dtype=dt)
+            keep.append(v)
+            return v
+
+        def scalar(name, default, cast):
+            return cast(np.asarray(a[name]).reshape(-1)[0]) if a.get(name) is not None else default
+
+        d = ws_c3dgs_arrays()
+        xyz = arr("xyz", np.float16).reshape(-1, 3)
+        opacity = arr("opacity", np.int8).reshape(-1)
+        n = len(xyz)
+        if len(opacity) != n:
+            raise WsError(-1, "websplat_b200: invalid argument (status -1): opacity has %d entries for %d points" % (len(opacity), n))
+        d.xyz, d.opacity, d.num_points = xyz.ctypes.data, opacity.ctypes.data, n
+        has_sf = a.get("scaling_factor_scale") is not None                                      # io/npz.rs:88-96
+        for name, dt in (("scaling_factor", np.int8), ("gaussian_indices", np.int32), ("feature_indices", np.int32)):
+            v = arr(name, dt, required=(name == "scaling_factor" and has_sf))
+            if name == "scaling_factor" and not has_sf:
+                v = None
+            if v is not None:
+                if v.size != n:
+                    raise WsError(-1, "websplat_b200: invalid argument (status -1): %s has %d entries for %d points" % (name, v.size, n))
+                setattr(d, name, v.ctypes.data)
+        scaling = arr("scaling", np.int8).reshape(-1, 3)
+        rotation = arr("rotation", np.int8).reshape(-1, 4)
+        if len(scaling) != len(rotation):
+            raise WsError(-1, "websplat_b200: invalid argument (status -1): scaling / rotation lengths differ")
+        d.scaling, d.rotation, d.num_covars = scaling.ctypes.data, rotation.ctypes.data, len(rotation)
+        dc = arr("features_dc", np.int8).reshape(-1, 3)
+        rest = arr("features_rest", np.int8)
+        # sh degree from features_rest.shape[1] + 1 (io/npz.rs:33-37)
+        ncoef = (rest.shape[1] + 1) if rest.ndim >= 2 else 1
+        deg = int(round(ncoef ** 0.5)) - 1
+        if (deg + 1) ** 2 != ncoef:
+            raise WsError(-1, "websplat_b200: invalid argument (status -1): num sh coefs not valid")
+        if rest.size != len(dc) * (ncoef - 1) * 3:
+            raise WsError(-1, "websplat_b200: invalid argument (status -1): features_rest / features_dc lengths differ")
+        d.features_dc, d.features_rest, d.num_features, d.sh_deg = dc.ctypes.data, rest.ctypes.data, len(dc), deg
+        d.scaling_scale, d.scaling_zero_point = scalar("scaling_scale", 1.0, float), scalar("scaling_zero_point", 0, int)
+        d.rotation_scale, d.rotation_zero_point = scalar("rotation_scale", 1.0, float), scalar("rotation_zero_point", 0, int)
+        for field, key in (("color_dc", "features_dc"), ("color_rest", "features_rest"), ("opacity", "opacity"), ("scaling_factor", "scaling_factor")):
+            qz = getattr(d.quantization, field)
+            qz.zero_point = scalar(key + "_zero_point", 0, int) if (key != "scaling_factor" or has_sf) else 0
+            qz.scale = scalar(key + "_scale", 1.0, float) if (key != "scaling_factor" or has_sf) else 1.0
+        if a.get("mip_splatting") is not None:
+            d.has_mip_splatting, d.mip_splatting = 1, int(bool(np.asarray(a["mip_splatting"]).reshape(-1)[0]))
+        if a.get("kernel_size") is not None:
+            d.has_kernel_size, d.kernel_size = 1, float(np.asarray(a["kernel_size"]).reshape(-1)[0])
+        if a.get("background_color") is not None:
+            d.has_background, d.background_color = 1, _f3(np.asarray(a["background_color"], np.float32).reshape(-1)[:3])
+        self = object.__new__(cls)
+        self._h = C.c_void_p()
+        self._ctx = ctx
+        _check(lib().ws_pointcloud_create_from_c3dgs(ctx._h, C.byref(d), C.byref(self._h)))
+        return self
+
+    def read(self, which):
+        """Debug read-back of the resident layouts: 'gaussians' (n, 28|24) u8, 'sh_coefs' (n, 96) u8 (raw) or the flat
+        i8 codebook (compressed), 'xyz' (n, 3) f32, 'covars' (K, 12) u8 (compressed)."""
+        idx = {"gaussians": 0, "sh_coefs": 1, "xyz": 2, "covars": 3}[which]
+        nbytes = lib().ws_pointcloud_buffer_bytes(self._h, idx)
+        out = np.zeros(nbytes, np.uint8)
+        _check(lib().ws_pointcloud_read(self._h, idx, out.ctypes.data, out.nbytes))
+        if idx == 0:
+            return out.reshape(-1, 24 if self.compressed() else 28)
+        if idx == 1:
+            return out.view(np.int8) if self.compressed() else out.reshape(-1, 96)
+        if idx == 2:
+            return out.view(np.float32).reshape(-1, 3)
+        return out.reshape(-1, 12)
+
+    def background_color(self):
+        o = (C.c_float * 3)()
+        return np.array(o[:], dtype=np.float32) if lib().ws_pointcloud_background_color(self._h, C.byref(o)) else None
+
     def num_points(self):
         return lib().ws_pointcloud_num_points(self._h)
 
@@ -559,6 +697,18 @@ class GaussianRenderer:
             self.close()
         except Exception:
             pass
+
+
+def ply_probe(data):
+    """Header-only parse of a .ply image (io/ply.rs:28-48); host code, no GPU needed."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    info = ws_ply_info()
+    _check(lib().ws_ply_probe(buf.ctypes.data if len(buf) else None, len(buf), C.byref(info)))
+    return dict(num_points=info.num_points, data_offset=info.data_offset, sh_deg=info.sh_deg, stride_bytes=info.stride_bytes,
+                big_endian=bool(info.big_endian),
+                mip_splatting=bool(info.mip_splatting) if info.has_mip_splatting else None,
+                kernel_size=info.kernel_size if info.has_kernel_size else None,
+                background_color=list(info.background_color) if info.has_background else None)
 
 
 def sort_pairs_host(ctx, keys, payload, key_bits=32):

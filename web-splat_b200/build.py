@@ -25,6 +25,7 @@ UNITS = {
     "binning.cu": [],
     "composite.cu": [],
     "shard.cu": [],
+    "ingest.cu": ["-fmad=false"],
     "capi.cu": [],
 }
 HEADERS = ["ws_device.cuh", "ws_kernels.h", os.path.join("..", "..", "include", "websplat_b200.h")]

@@ -16,7 +16,9 @@
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
+#include <ctype.h>
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 #include <new>
@@ -185,6 +187,8 @@ struct ws_pointcloud {
     int32_t has_mip, mip;
     int32_t has_kernel; float kernel;
     int32_t has_bg; float bg[3];
+    size_t sh_bytes = 0;           // bytes of SH payload in d_sh (read-back)
+    uint32_t num_covars = 0;
 };
 
 extern "C" void ws_pointcloud_destroy(ws_pointcloud *pc)
@@ -235,6 +239,7 @@ extern "C" ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_d
     PC_CU(cudaMalloc(&pc->d_sh, shb + 32u));
     PC_CU(cudaMemset(pc->d_sh, 0, shb + 32u));
     if (d->sh_bytes) PC_CU(cudaMemcpy(pc->d_sh, d->sh_coefs, (size_t)d->sh_bytes, cudaMemcpyHostToDevice));
+    pc->sh_bytes = d->compressed ? (size_t)d->sh_bytes : (size_t)n * 96u; pc->num_covars = (uint32_t)d->num_covars;
     if (d->compressed) {
         const size_t cb = (size_t)d->num_covars * 12u;
         PC_CU(cudaMalloc(&pc->d_covars, cb ? cb : 16u));
@@ -242,6 +247,358 @@ extern "C" ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_d
     }
 #undef PC_CU
     *out = pc;
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// .ply ingest: PlyReader::new / read (io/ply.rs:28-48,165-195) +
+// GenericGaussianPointCloud::new (io/mod.rs:63-105).  The header is parsed here; the vertex block is
+// uploaded untouched and converted by ply.cu's kernel.
+namespace {
+struct PlyHeader {
+    size_t data_offset = 0;
+    uint64_t num_vertices = 0;
+    uint32_t num_props = 0, num_f = 0;
+    bool have_vertex = false, big_endian = false, ascii = false, non_float = false, layout_ok = true;
+    int32_t has_mip = 0, mip = 0, has_kernel = 0, has_bg = 0;
+    float kernel = 0.f, bg[3] = {0.f, 0.f, 0.f};
+    bool bad_comment = false;
+};
+std::string trimmed(const std::string &t)
+{
+    size_t a = 0, b = t.size();
+    while (a < b && isspace((unsigned char)t[a])) a++;
+    while (b > a && isspace((unsigned char)t[b - 1])) b--;
+    return t.substr(a, b - a);
+}
+std::string after_last_eq(const std::string &c)
+{
+    const size_t p = c.rfind('=');
+    return trimmed(p == std::string::npos ? c : c.substr(p + 1));
+}
+bool parse_f32(const std::string &t, float *out)
+{
+    if (t.empty()) return false;
+    char *end = nullptr;
+    const float v = strtof(t.c_str(), &end);
+    if (end == t.c_str() || *end != 0) return false;
+    *out = v; return true;
+}
+// returns false when no complete header is found
+bool parse_ply_header(const uint8_t *bytes, size_t len, PlyHeader *h)
+{
+    size_t pos = 0;
+    int line_no = 0;
+    std::string element;
+    // the fixed property order read_line assumes (io/ply.rs:50-100)
+    static const char *kHead[9] = {"x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"};
+    std::vector<std::string> props;
+    while (pos < len) {
+        size_t e = pos;
+        while (e < len && bytes[e] != '\n') e++;
+        if (e == len) return false;
+        std::string line(reinterpret_cast<const char *>(bytes + pos), e - pos);
+        pos = e + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        line_no++;
+        if (line_no == 1) { if (trimmed(line) != "ply") return false; continue; }
+        if (line == "end_header") { h->data_offset = pos; break; }
+        if (line.rfind("format ", 0) == 0) {
+            h->big_endian = line.find("binary_big_endian") != std::string::npos;
+            h->ascii = line.find("ascii") != std::string::npos;
+        } else if (line.rfind("comment", 0) == 0) {
+            const std::string c = trimmed(line.substr(7));
+            // first matching comment wins, like Iterator::find (io/ply.rs:121-160)
+            if (c.find("mip") != std::string::npos && !h->has_mip && !h->bad_comment) {
+                const std::string v = after_last_eq(c);
+                if (v == "true") { h->has_mip = 1; h->mip = 1; }
+                else if (v == "false") { h->has_mip = 1; h->mip = 0; }
+                else h->bad_comment = true;
+            }
+            if (c.find("kernel_size") != std::string::npos && !h->has_kernel) {
+                if (parse_f32(after_last_eq(c), &h->kernel)) h->has_kernel = 1; else h->bad_comment = true;
+            }
+            if (c.find("background_color") != std::string::npos && !h->has_bg) {
+                // a malformed background only warns in the reference (io/ply.rs:37-39): leave it unset
+                const std::string v = after_last_eq(c);
+                float rgb[3]; int k = 0; size_t a = 0; bool ok = true;
+                while (ok && a <= v.size()) {
+                    size_t b = v.find(',', a);
+                    if (b == std::string::npos) b = v.size();
+                    float f;
+                    if (!parse_f32(trimmed(v.substr(a, b - a)), &f)) ok = false;
+                    else if (k < 3) rgb[k++] = f; else k++;
+                    a = b + 1;
+                }
+                if (ok && k >= 3) { h->has_bg = 1; memcpy(h->bg, rgb, sizeof rgb); }
+            }
+        } else if (line.rfind("element ", 0) == 0) {
+            char name[64]; unsigned long long cnt = 0;
+            if (sscanf(line.c_str(), "element %63s %llu", name, &cnt) == 2) {
+                element = name;
+                if (element == "vertex") { h->have_vertex = true; h->num_vertices = cnt; }
+            }
+        } else if (line.rfind("property ", 0) == 0 && element == "vertex") {
+            char type[64], name[128];
+            if (sscanf(line.c_str(), "property %63s %127s", type, name) == 2) {
+                if (strcmp(type, "float") != 0 && strcmp(type, "float32") != 0) h->non_float = true;
+                props.push_back(name);
+                if (strncmp(name, "f_", 2) == 0) h->num_f++;
+            }
+        }
+    }
+    if (!h->data_offset) return false;
+    h->num_props = (uint32_t)props.size();
+    for (size_t i = 0; i < 9 && i < props.size(); i++) if (props[i] != kHead[i]) h->layout_ok = false;
+    if (props.size() >= 8) {
+        static const char *kTail[8] = {"opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"};
+        for (size_t i = 0; i < 8; i++) if (props[props.size() - 8 + i] != kTail[i]) h->layout_ok = false;
+    }
+    return true;
+}
+inline float ord2f(uint32_t o) { uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; float f; memcpy(&f, &u, 4); return f; }
+}  // namespace
+
+// GenericGaussianPointCloud::new / new_compressed statistics from the device reductions
+static void finish_cloud_stats(ws_pointcloud *pc, uint32_t n, const double sums[9], const uint32_t mm[6], float box0)
+{
+    // bounding box: Aabb::zeroed() (raw, io/mod.rs:74-77) or Aabb::unit() (compressed, io/mod.rs:119-122)
+    // grown by every point
+    for (int d = 0; d < 3; d++) {
+        const float lo = n ? ord2f(mm[d]) : -box0, hi = n ? ord2f(mm[3 + d]) : box0;
+        pc->aabb.min[d] = fminf(-box0, lo); pc->aabb.max[d] = fmaxf(box0, hi);
+    }
+    // centroid + plane normal (plane_from_points, io/mod.rs:185-284) from f64 moments; the reference
+    // accumulates in f32 in file order, so the last digits differ -- neither is on the render path
+    // (centroid only feeds the intro reveal, `up` only the viewer's controller)
+    const double inv_n = n ? 1.0 / (double)n : 0.0;
+    const double cx = sums[0] * inv_n, cy = sums[1] * inv_n, cz = sums[2] * inv_n;
+    pc->center[0] = (float)cx; pc->center[1] = (float)cy; pc->center[2] = (float)cz;
+    if (!n) { const float qnan = nanf(""); pc->center[0] = pc->center[1] = pc->center[2] = qnan; }   // 0 * (1/0)
+    pc->has_up = 0; pc->up[0] = pc->up[1] = pc->up[2] = 0.f;
+    if (n >= 3) {
+        const double xx = sums[3] * inv_n - cx * cx, xy = sums[4] * inv_n - cx * cy, xz = sums[5] * inv_n - cx * cz;
+        const double yy = sums[6] * inv_n - cy * cy, yz = sums[7] * inv_n - cy * cz, zz = sums[8] * inv_n - cz * cz;
+        double w[3] = {0, 0, 0};
+        const double dets[3] = {yy * zz - yz * yz, xx * zz - xz * xz, xx * yy - xy * xy};
+        const double axes[3][3] = {{dets[0], xz * yz - xy * zz, xy * yz - xz * yy},
+                                   {xz * yz - xy * zz, dets[1], xy * xz - yz * xx},
+                                   {xy * yz - xz * yy, xy * xz - yz * xx, dets[2]}};
+        for (int k = 0; k < 3; k++) {
+            double weight = dets[k] * dets[k];
+            if (w[0] * axes[k][0] + w[1] * axes[k][1] + w[2] * axes[k][2] < 0.0) weight = -weight;
+            for (int d = 0; d < 3; d++) w[d] += axes[k][d] * weight;
+        }
+        const double mag = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        double nrm[3] = {w[0] / mag, w[1] / mag, w[2] / mag};
+        if (nrm[1] < 0.0) for (int d = 0; d < 3; d++) nrm[d] = -nrm[d];
+        if (isfinite(nrm[0]) && isfinite(nrm[1]) && isfinite(nrm[2])) {
+            pc->has_up = 1;
+            for (int d = 0; d < 3; d++) pc->up[d] = (float)nrm[d];
+        }
+    }
+    {   // `if bbox.radius() < 10. { up = None; }` (io/mod.rs:87-89)
+        const float dx = pc->aabb.max[0] - pc->aabb.min[0], dy = pc->aabb.max[1] - pc->aabb.min[1], dz = pc->aabb.max[2] - pc->aabb.min[2];
+        if (sqrtf(dx * dx + dy * dy + dz * dz) / 2.f < 10.f) pc->has_up = 0;
+    }
+}
+
+static ws_status check_ply_header(const uint8_t *bytes, uint64_t file_len, PlyHeader *h, uint32_t *sh_deg_out)
+{
+    if (!parse_ply_header(bytes, (size_t)file_len, h)) return fail(WS_ERR_INVALID_ARGUMENT, "not a .ply file / truncated header");
+    if (!h->have_vertex) return fail(WS_ERR_INVALID_ARGUMENT, "missing element vertex");
+    if (h->ascii) return fail(WS_ERR_UNSUPPORTED, "ascii ply format not supported");                 // io/ply.rs:181
+    if (h->bad_comment) return fail(WS_ERR_INVALID_ARGUMENT, "could not parse a mip / kernel_size comment");
+    if (h->num_f % 3u) return fail(WS_ERR_INVALID_ARGUMENT, "number of f_* properties is not a multiple of 3");
+    const uint32_t ncoef = h->num_f / 3u;
+    uint32_t root = 0;
+    while (root * root < ncoef) root++;
+    if (root * root != ncoef || root == 0) return fail(WS_ERR_INVALID_ARGUMENT, "number of sh coefficients cannot be mapped to sh degree");   // utils.rs:183-189
+    if (root - 1u > 3) return fail(WS_ERR_UNSUPPORTED, "sh degree > 3");
+    if (h->non_float || !h->layout_ok || h->num_props != 14u + 3u * ncoef)
+        return fail(WS_ERR_UNSUPPORTED, "vertex properties are not the 3DGS layout x,y,z,nx,ny,nz,f_dc_*,f_rest_*,opacity,scale_*,rot_* (all float)");
+    if (h->num_vertices >= (1ull << 30)) return fail(WS_ERR_UNSUPPORTED, "more than 2^30 - 1 points");
+    if ((uint64_t)h->data_offset + h->num_vertices * (uint64_t)(h->num_props * 4u) > file_len) return fail(WS_ERR_INVALID_ARGUMENT, "vertex data truncated");
+    *sh_deg_out = root - 1u;
+    return WS_OK;
+}
+
+extern "C" ws_status ws_ply_probe(const void *file_bytes, uint64_t file_len, ws_ply_info *out)
+{
+    if (!out || (!file_bytes && file_len)) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    memset(out, 0, sizeof *out);
+    PlyHeader h; uint32_t sh_deg = 0;
+    const ws_status s = check_ply_header(static_cast<const uint8_t *>(file_bytes), file_len, &h, &sh_deg);
+    if (s != WS_OK) return s;
+    out->num_points = h.num_vertices; out->data_offset = h.data_offset;
+    out->sh_deg = sh_deg; out->stride_bytes = h.num_props * 4u; out->big_endian = h.big_endian;
+    out->has_mip_splatting = h.has_mip; out->mip_splatting = h.mip;
+    out->has_kernel_size = h.has_kernel; out->kernel_size = h.kernel;
+    out->has_background = h.has_bg; memcpy(out->background_color, h.bg, sizeof h.bg);
+    return WS_OK;
+}
+
+extern "C" ws_status ws_pointcloud_create_from_ply(ws_context *ctx, const void *file_bytes, uint64_t file_len, ws_pointcloud **out)
+{
+    if (!ctx || !out || (!file_bytes && file_len)) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    const uint8_t *bytes = static_cast<const uint8_t *>(file_bytes);
+    PlyHeader h; uint32_t sh_deg = 0;
+    {
+        const ws_status hs = check_ply_header(bytes, file_len, &h, &sh_deg);
+        if (hs != WS_OK) return hs;
+    }
+    const uint32_t n = (uint32_t)h.num_vertices;
+    const uint32_t stride = h.num_props * 4u;
+
+    CU(cudaSetDevice(ctx->device));
+    ws_pointcloud *pc = new (std::nothrow) ws_pointcloud();
+    if (!pc) return fail(WS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    pc->ctx = ctx; pc->n = n; pc->sh_deg = sh_deg; pc->compressed = false;
+    memset(&pc->quant, 0, sizeof pc->quant);
+    pc->has_mip = h.has_mip; pc->mip = h.mip;
+    pc->has_kernel = h.has_kernel; pc->kernel = h.kernel;
+    pc->has_bg = h.has_bg; memcpy(pc->bg, h.bg, sizeof pc->bg);
+    const size_t padded = ((size_t)n + 255u) / 256u * 256u;
+    const size_t slots = padded ? padded : 256u;
+    pc->sh_bytes = (size_t)n * 96u;
+    uint8_t *d_raw = nullptr; double *d_sums = nullptr; uint32_t *d_mm = nullptr;
+    cudaError_t e;
+#define PLY_CU(call) do { e = (call); if (e != cudaSuccess) { ws_status s__ = fail_cuda(e, #call); cudaFree(d_raw); cudaFree(d_sums); ws_pointcloud_destroy(pc); return s__; } } while (0)
+    PLY_CU(cudaMalloc(&pc->d_gaussians, slots * 28u));
+    PLY_CU(cudaMemset(pc->d_gaussians, 0, slots * 28u));
+    PLY_CU(cudaMalloc(&pc->d_sh, slots * 96u + 32u));
+    PLY_CU(cudaMemset(pc->d_sh, 0, slots * 96u + 32u));
+    PLY_CU(cudaMalloc(&pc->d_xyz, (size_t)(n ? n : 1) * 12u));
+    PLY_CU(cudaMalloc(&d_sums, 9 * sizeof(double) + 8 * sizeof(uint32_t)));
+    d_mm = reinterpret_cast<uint32_t *>(d_sums + 9);
+    PLY_CU(cudaMemset(d_sums, 0, 9 * sizeof(double) + 8 * sizeof(uint32_t)));
+    PLY_CU(cudaMemset(d_mm, 0xff, 3 * sizeof(uint32_t)));
+    double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t mm[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+    if (n) {
+        PLY_CU(cudaMalloc(&d_raw, (size_t)n * stride));
+        PLY_CU(cudaMemcpy(d_raw, bytes + h.data_offset, (size_t)n * stride, cudaMemcpyHostToDevice));
+        PlyConvertArgs a;
+        a.vertices = d_raw; a.n = n; a.stride_bytes = stride; a.sh_deg = sh_deg; a.big_endian = h.big_endian ? 1u : 0u;
+        a.gaussians = pc->d_gaussians; a.sh_coefs = pc->d_sh; a.xyz = pc->d_xyz; a.sums = d_sums; a.minmax = d_mm;
+        const unsigned want = (n + 255u) / 256u, cap = (unsigned)ctx->sm_count * 8u;
+        PLY_CU(launch_ply_convert(a, (int)(want < cap ? want : cap), 0));
+        PLY_CU(cudaMemcpy(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost));
+        PLY_CU(cudaMemcpy(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost));
+    }
+#undef PLY_CU
+    cudaFree(d_raw); cudaFree(d_sums);
+    finish_cloud_stats(pc, n, sums, mm, 0.f);
+    *out = pc;
+    return WS_OK;
+}
+
+// .npz ingest: the array post-processing of NpzReader::read (io/npz.rs:58-225)
+// + GenericGaussianPointCloud::new_compressed (io/mod.rs:107-150) on the GPU.
+extern "C" ws_status ws_pointcloud_create_from_c3dgs(ws_context *ctx, const ws_c3dgs_arrays *d, ws_pointcloud **out)
+{
+    if (!ctx || !d || !out) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if (d->sh_deg > 3) return fail(WS_ERR_INVALID_ARGUMENT, "sh_deg > 3");
+    if (d->num_points >= (1ull << 30) || d->num_covars >= (1ull << 30) || d->num_features >= (1ull << 30))
+        return fail(WS_ERR_UNSUPPORTED, "more than 2^30 - 1 entries");
+    if (d->num_points && (!d->xyz || !d->opacity)) return fail(WS_ERR_INVALID_ARGUMENT, "xyz / opacity is NULL");
+    if (d->num_covars && (!d->scaling || !d->rotation)) return fail(WS_ERR_INVALID_ARGUMENT, "scaling / rotation is NULL");
+    if (d->num_features && (!d->features_dc || (d->sh_deg > 0 && !d->features_rest))) return fail(WS_ERR_INVALID_ARGUMENT, "features_dc / features_rest is NULL");
+    // without index arrays entry i belongs to point i (io/npz.rs:179-186)
+    if (!d->gaussian_indices && d->num_covars < d->num_points) return fail(WS_ERR_INVALID_ARGUMENT, "no gaussian_indices and fewer covariances than points");
+    if (!d->feature_indices && d->num_features < d->num_points) return fail(WS_ERR_INVALID_ARGUMENT, "no feature_indices and fewer SH entries than points");
+    const uint32_t n = (uint32_t)d->num_points, nc = (uint32_t)d->num_covars, nf = (uint32_t)d->num_features;
+    const uint32_t per = (d->sh_deg + 1u) * (d->sh_deg + 1u) * 3u;
+
+    CU(cudaSetDevice(ctx->device));
+    ws_pointcloud *pc = new (std::nothrow) ws_pointcloud();
+    if (!pc) return fail(WS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    pc->ctx = ctx; pc->n = n; pc->sh_deg = d->sh_deg; pc->compressed = true;
+    memcpy(&pc->quant, &d->quantization, sizeof pc->quant);
+    pc->has_mip = d->has_mip_splatting; pc->mip = d->mip_splatting;
+    pc->has_kernel = d->has_kernel_size; pc->kernel = d->kernel_size;
+    pc->has_bg = d->has_background; memcpy(pc->bg, d->background_color, sizeof pc->bg);
+    const size_t padded = ((size_t)n + 255u) / 256u * 256u;
+    const size_t slots = padded ? padded : 256u;
+    // one staging allocation for all input arrays, 16-B aligned slices
+    struct Slice { const void *src; size_t bytes, off; };
+    Slice in[9] = {{d->xyz, (size_t)n * 6u, 0}, {d->opacity, (size_t)n, 0}, {d->scaling_factor, d->scaling_factor ? (size_t)n : 0u, 0},
+                   {d->gaussian_indices, d->gaussian_indices ? (size_t)n * 4u : 0u, 0}, {d->feature_indices, d->feature_indices ? (size_t)n * 4u : 0u, 0},
+                   {d->scaling, (size_t)nc * 3u, 0}, {d->rotation, (size_t)nc * 4u, 0},
+                   {d->features_dc, (size_t)nf * 3u, 0}, {d->features_rest, (size_t)nf * (per - 3u), 0}};
+    size_t total = 0;
+    for (auto &sl : in) { sl.off = total; total += (sl.bytes + 15u) / 16u * 16u; }
+    uint8_t *d_in = nullptr; double *d_sums = nullptr;
+    cudaError_t e;
+#define NPZ_CU(call) do { e = (call); if (e != cudaSuccess) { ws_status s__ = fail_cuda(e, #call); cudaFree(d_in); cudaFree(d_sums); ws_pointcloud_destroy(pc); return s__; } } while (0)
+    NPZ_CU(cudaMalloc(&d_in, total ? total : 16u));
+    for (auto &sl : in) if (sl.bytes) NPZ_CU(cudaMemcpy(d_in + sl.off, sl.src, sl.bytes, cudaMemcpyHostToDevice));
+    NPZ_CU(cudaMalloc(&pc->d_gaussians, slots * 24u));
+    NPZ_CU(cudaMemset(pc->d_gaussians, 0, slots * 24u));
+    const size_t shb = (size_t)nf * per;
+    NPZ_CU(cudaMalloc(&pc->d_sh, (shb ? shb : 32u) + 32u));
+    NPZ_CU(cudaMemset(pc->d_sh, 0, (shb ? shb : 32u) + 32u));
+    NPZ_CU(cudaMalloc(&pc->d_covars, nc ? (size_t)nc * 12u : 16u));
+    NPZ_CU(cudaMalloc(&pc->d_xyz, (size_t)(n ? n : 1) * 12u));
+    NPZ_CU(cudaMalloc(&d_sums, 9 * sizeof(double) + 8 * sizeof(uint32_t)));
+    uint32_t *d_mm = reinterpret_cast<uint32_t *>(d_sums + 9);
+    NPZ_CU(cudaMemset(d_sums, 0, 9 * sizeof(double) + 8 * sizeof(uint32_t)));
+    NPZ_CU(cudaMemset(d_mm, 0xff, 3 * sizeof(uint32_t)));
+    C3dgsArgs a;
+    a.xyz_f16 = reinterpret_cast<const uint16_t *>(d_in + in[0].off);
+    a.opacity = reinterpret_cast<const int8_t *>(d_in + in[1].off);
+    a.scaling_factor = d->scaling_factor ? reinterpret_cast<const int8_t *>(d_in + in[2].off) : nullptr;
+    a.gaussian_indices = d->gaussian_indices ? reinterpret_cast<const int32_t *>(d_in + in[3].off) : nullptr;
+    a.feature_indices = d->feature_indices ? reinterpret_cast<const int32_t *>(d_in + in[4].off) : nullptr;
+    a.scaling = reinterpret_cast<const int8_t *>(d_in + in[5].off);
+    a.rotation = reinterpret_cast<const int8_t *>(d_in + in[6].off);
+    a.features_dc = reinterpret_cast<const int8_t *>(d_in + in[7].off);
+    a.features_rest = reinterpret_cast<const int8_t *>(d_in + in[8].off);
+    a.n = n; a.num_covars = nc; a.num_features = nf; a.sh_deg = d->sh_deg;
+    a.scaling_scale = d->scaling_scale; a.scaling_zero_point = (float)d->scaling_zero_point;       // `as f32`, io/npz.rs:66-72
+    a.rotation_scale = d->rotation_scale; a.rotation_zero_point = (float)d->rotation_zero_point;
+    a.gaussians = pc->d_gaussians; a.sh_out = reinterpret_cast<int8_t *>(pc->d_sh); a.covars = pc->d_covars; a.xyz = pc->d_xyz;
+    a.sums = d_sums; a.minmax = d_mm;
+    NPZ_CU(launch_c3dgs_convert(a, ctx->sm_count * 8, 0));
+    double sums[9]; uint32_t mm[6];
+    NPZ_CU(cudaMemcpy(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost));
+    NPZ_CU(cudaMemcpy(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost));
+#undef NPZ_CU
+    cudaFree(d_in); cudaFree(d_sums);
+    pc->sh_bytes = shb; pc->num_covars = nc;
+    finish_cloud_stats(pc, n, sums, mm, 1.f);
+    *out = pc;
+    return WS_OK;
+}
+
+extern "C" uint64_t ws_pointcloud_buffer_bytes(const ws_pointcloud *pc, int32_t which)
+{
+    if (!pc) return 0;
+    switch (which) {
+    case 0: return (uint64_t)pc->n * (pc->compressed ? 24u : 28u);
+    case 1: return pc->compressed ? pc->sh_bytes : (uint64_t)pc->n * 96u;
+    case 2: return (uint64_t)pc->n * 12u;
+    case 3: return (uint64_t)pc->num_covars * 12u;
+    default: return 0;
+    }
+}
+
+extern "C" ws_status ws_pointcloud_read(const ws_pointcloud *pc, int32_t which, void *dst, uint64_t dst_bytes)
+{
+    if (!pc || (!dst && dst_bytes)) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    const void *src = nullptr; size_t bytes = 0;
+    switch (which) {
+    case 0: src = pc->d_gaussians; bytes = (size_t)pc->n * (pc->compressed ? 24u : 28u); break;
+    case 1: src = pc->d_sh; bytes = pc->compressed ? pc->sh_bytes : (size_t)pc->n * 96u; break;
+    case 2: src = pc->d_xyz; bytes = (size_t)pc->n * 12u; break;
+    case 3: src = pc->d_covars; bytes = (size_t)pc->num_covars * 12u; break;
+    default: return fail(WS_ERR_INVALID_ARGUMENT, "unknown point-cloud buffer");
+    }
+    if (dst_bytes < bytes) return fail(WS_ERR_INVALID_ARGUMENT, "destination too small");
+    CU(cudaSetDevice(pc->ctx->device));
+    if (bytes) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return WS_OK;
 }
 
@@ -263,6 +620,12 @@ extern "C" int32_t ws_pointcloud_up(const ws_pointcloud *pc, float out[3])
     if (!pc) return 0;
     if (pc->has_up && out) memcpy(out, pc->up, 12);
     return pc->has_up;
+}
+extern "C" int32_t ws_pointcloud_background_color(const ws_pointcloud *pc, float out[3])
+{
+    if (!pc) return 0;
+    if (pc->has_bg && out) memcpy(out, pc->bg, 12);
+    return pc->has_bg;
 }
 extern "C" int32_t ws_pointcloud_mip_splatting(const ws_pointcloud *pc, int32_t *out)
 {

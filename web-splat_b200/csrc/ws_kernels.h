@@ -85,6 +85,37 @@ struct CompositeArgs {
 };
 cudaError_t launch_composite(const CompositeArgs &a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream);
 
+// ---- file-format ingest (ingest.cu) ---------------------------------------------------------------------------
+struct PlyConvertArgs {
+    const uint8_t *vertices;      // the file's vertex block, uploaded as is
+    uint32_t n, stride_bytes, sh_deg, big_endian;
+    uint8_t *gaussians;           // out: n x 28 B
+    uint8_t *sh_coefs;            // out: n x 96 B
+    float *xyz;                   // out: n x 3
+    double *sums;                 // out: [9] sum x,y,z, xx,xy,xz,yy,yz,zz (zeroed by the caller)
+    uint32_t *minmax;             // out: [6] ordered-int min xyz / max xyz (min = 0xffffffff, max = 0 by the caller)
+};
+cudaError_t launch_ply_convert(const PlyConvertArgs &a, int grid, cudaStream_t stream);
+
+struct C3dgsArgs {                // device copies of the .npz arrays (io/npz.rs:58-160)
+    const uint16_t *xyz_f16;      // n x 3 f16
+    const int8_t *opacity;        // n
+    const int8_t *scaling_factor; // n or NULL
+    const int32_t *gaussian_indices, *feature_indices;   // n or NULL (identity)
+    const int8_t *scaling;        // num_covars x 3
+    const int8_t *rotation;       // num_covars x 4
+    const int8_t *features_dc;    // num_features x 3
+    const int8_t *features_rest;  // num_features x (3C - 3)
+    uint32_t n, num_covars, num_features, sh_deg;
+    float scaling_scale, scaling_zero_point, rotation_scale, rotation_zero_point;
+    uint8_t *gaussians;           // out: n x 24 B
+    int8_t *sh_out;               // out: num_features x 3C
+    uint8_t *covars;              // out: num_covars x 12 B
+    float *xyz;                   // out: n x 3
+    double *sums; uint32_t *minmax;
+};
+cudaError_t launch_c3dgs_convert(const C3dgsArgs &a, int max_grid, cudaStream_t stream);
+
 // ---- multi-GPU exchange (shard.cu) ---------------------------------------------------------------
 struct RouteArgs {
     const uint32_t *l_splats, *l_keys; const uint2 *l_rects;   // stage-1 output of the local shard (slot order)

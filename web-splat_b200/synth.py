@@ -189,3 +189,85 @@ def orbit_camera(az_deg, radius=3.0, elev_deg=15.0):
 
 def orbit_views(count=36):
     return [orbit_camera(360.0 * i / count) for i in range(count)]
+
+
+# ---- synthetic .ply files (the 3DGS training-output format io/ply.rs reads) ---------------------------
+def ply_vertices(n, seed, sh_deg=3, spread=1.0):
+    """(n, 14 + 3*(sh_deg+1)^2) float32 vertex block in the property order read_line assumes
+    (io/ply.rs:50-100): x y z nx ny nz f_dc[3] f_rest[3][C-1] opacity(logit) scale(log)[3] rot(wxyz, unnormalised)[4]."""
+    xyz, scale, q, opacity, sh = _attributes(n, seed)
+    rng = np.random.default_rng(seed + 1234)
+    C_ = (sh_deg + 1) ** 2
+    v = np.zeros((n, 14 + 3 * C_), np.float32)
+    v[:, 0:3] = xyz * np.float32(spread)
+    v[:, 3:6] = rng.standard_normal((n, 3)).astype(np.float32)          # normals: present in the file, never used
+    v[:, 6:9] = sh[:, 0, :]
+    v[:, 9:9 + 3 * (C_ - 1)] = sh[:, 1:C_, :].transpose(0, 2, 1).reshape(n, -1)   # channel-major [3][C-1]
+    k = 9 + 3 * (C_ - 1)
+    with np.errstate(divide="ignore"):
+        v[:, k] = np.log(opacity / (1.0 - opacity))
+    v[:, k + 1:k + 4] = np.log(scale * np.float32(spread))
+    v[:, k + 4:k + 8] = q * rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)   # training output is not unit length
+    return v
+
+
+def ply_bytes(vertices, sh_deg, comments=(), big_endian=False, fmt=None):
+    """Serialise a vertex block into a .ply file image (header + binary body)."""
+    C_ = (sh_deg + 1) ** 2
+    names = ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"]
+    names += ["f_rest_%d" % i for i in range(3 * (C_ - 1))]
+    names += ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    assert vertices.shape[1] == len(names)
+    fmt = fmt or ("binary_big_endian" if big_endian else "binary_little_endian")
+    head = ["ply", "format %s 1.0" % fmt] + ["comment %s" % c for c in comments]
+    head += ["element vertex %d" % len(vertices)] + ["property float %s" % nm for nm in names] + ["end_header"]
+    body = np.ascontiguousarray(vertices, dtype=">f4" if big_endian else "<f4").tobytes()
+    return ("\n".join(head) + "\n").encode("ascii") + body
+
+
+# ---- synthetic compressed .npz members (what io/npz.rs reads) -----------------------------------------
+def c3dgs_arrays(n, seed, sh_deg=3, codebook=4096, scaling_factor=True, indices=True, metadata=True):
+    """dict of the arrays a c3dgs .npz holds (io/npz.rs:58-160).  scaling_factor=False gives the older variant
+    whose `scaling` is the quantised log-scale; indices=False the variant with one codebook entry per point."""
+    xyz, scale, q, opacity, sh = _attributes(n, seed)
+    rng = np.random.default_rng(seed + 99)
+    k = min(codebook, max(n, 1)) if indices else n
+    pick_g = rng.integers(0, max(n, 1), size=k) if (indices and n) else np.arange(k)
+    pick_s = rng.integers(0, max(n, 1), size=k) if (indices and n) else np.arange(k)
+    C_ = (sh_deg + 1) ** 2
+
+    def quant(v, lo, hi):
+        sc = (hi - lo) / 255.0
+        zp = int(round(-128 - lo / sc))
+        return np.clip(np.round(np.asarray(v, np.float64) / sc + zp), -128, 127).astype(np.int8), zp, np.float32(sc)
+
+    out = {"xyz": xyz.astype(np.float16)}
+    out["opacity"], out["opacity_zero_point"], out["opacity_scale"] = quant(opacity[:, None], 0.0, 1.0)
+    norm = np.linalg.norm(scale, axis=1)
+    if scaling_factor:
+        logs = np.log(norm)
+        out["scaling_factor"], out["scaling_factor_zero_point"], out["scaling_factor_scale"] = quant(
+            logs[:, None], float(logs.min()) if n else -1.0, float(logs.max()) if n else 1.0)
+        out["scaling"], out["scaling_zero_point"], out["scaling_scale"] = quant((scale / norm[:, None])[pick_g], -0.1, 1.0)
+    else:
+        ls = np.log(scale[pick_g])
+        out["scaling"], out["scaling_zero_point"], out["scaling_scale"] = quant(ls, float(ls.min()) if n else -1.0, float(ls.max()) if n else 1.0)
+    out["rotation"], out["rotation_zero_point"], out["rotation_scale"] = quant(q[pick_g], -1.0, 1.0)
+    out["features_dc"], out["features_dc_zero_point"], out["features_dc_scale"] = quant(sh[pick_s][:, 0:1, :], -4.0, 4.0)
+    out["features_rest"], out["features_rest_zero_point"], out["features_rest_scale"] = quant(sh[pick_s][:, 1:C_, :], -0.5, 0.5)
+    if indices:
+        out["gaussian_indices"] = rng.integers(0, k, size=n).astype(np.int32)
+        out["feature_indices"] = rng.integers(0, k, size=n).astype(np.int32)
+    if metadata:
+        out["kernel_size"] = np.float32(0.1)
+        out["mip_splatting"] = np.bool_(True)
+        out["background_color"] = np.array([0.0, 0.0, 0.0], np.float32)
+    return out
+
+
+def npz_bytes(arrays):
+    """Serialise the members into a .npz file image."""
+    import io
+    f = io.BytesIO()
+    np.savez(f, **arrays)
+    return f.getvalue()
