@@ -90,7 +90,7 @@ def test_gpu_npz_ingest_matches_oracle(ws, orc, ctx, sf, idx, deg):
 @pytest.mark.gpu
 def test_gpu_npz_cloud_renders_like_the_uploaded_cloud(ws, orc, ctx):
     n, W, H = 30000, 640, 360
-    a = ws.synth.c3dgs_arrays(n, 5, 3, codebook=4096)
+    a = ws.synth.c3dgs_arrays(n, 5, 3, codebook=4096, metadata=False)      # metadata would change the resolved settings
     pc_npz = ws.PointCloud.from_npz(ctx, a)                               # already-decoded members
     o = orc.c3dgs_convert(a)
     zp = lambda k: (int(a[k + "_zero_point"]), np.float32(a[k + "_scale"]))

@@ -721,5 +721,6 @@ def sort_pairs_host(ctx, keys, payload, key_bits=32):
     return keys, payload
 
 
-from . import synth  # noqa: E402,F401
+from . import scene, synth  # noqa: E402,F401
+from .scene import Scene, SceneCamera  # noqa: E402,F401
 from .distributed import ShardedRenderer, shard_cloud, tile_row_bands  # noqa: E402,F401
