@@ -104,5 +104,6 @@ def test_gpu_offline_renderer_end_to_end(ws, orc, ctx, tmp_path):
     cloud = dict(gaussians=o["gaussians"].view(ws.synth.GAUSSIAN_DTYPE).reshape(-1), sh_coefs=o["sh_coefs"].view(np.float16).reshape(-1, 16, 3),
                  num_points=n, sh_deg=3, compressed=False, aabb_min=o["bbox"][:3], aabb_max=o["bbox"][3:], center=o["center"])
     ref = orc.render_frame(cloud, cam.position, cam.rotation, W, H, cam.projection.fovx, cam.projection.fovy)
-    assert np.abs(frame.astype(np.float32) - ref["image"]).mean() < 3e-5
+    # the frame is f16 (half an ulp at 0.5 is 1.2e-4), the oracle image f32
+    assert np.abs(frame.astype(np.float32) - ref["image"]).mean() < 1.5e-4
     assert np.abs(png.astype(np.int32) - ws.scene.frame_to_rgba8(ref["image"].astype(np.float16)).astype(np.int32)).max() <= 2
