@@ -121,4 +121,4 @@ def test_gpu_npz_cloud_renders_like_the_uploaded_cloud(ws, orc, ctx):
                   covars=o["covars"].view(np.float16).reshape(-1, 6))
     ref = orc.render_frame(ocloud, pos, rot, W, H, fovx, fovy)
     img = frames[0].astype(np.float32)
-    assert np.abs(img - ref["image"]).mean() < 2e-5
+    assert np.abs(img - ref["image"]).mean() < 1.5e-4              # f16 frame against the oracle's f32 image
