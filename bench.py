@@ -206,35 +206,51 @@ def run_ours(args):
                                        compressed=cloud["compressed"], covars=cloud.get("covars"),
                                        quantization=cloud.get("quantization"))
     pc = ws.PointCloud.new(ctx, gen)
-    r = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
-    r.set_pair_capacity(min(max(8 * cloud["num_points"], 1 << 22), (1 << 30) - 1))
+    # `depth` frames in flight: one renderer (own scratch) + one stream + one target per frame slot, all reading the
+    # same resident cloud; frame i runs in slot i % depth.  At the small configurations one frame's kernels are
+    # latency-bound and a second frame fills the idle SMs (cfg1 +36 %, cfg2 +22 %, cfg3 +2 %: profiles/r01o_*).
+    depth = max(1, int(args.frames_in_flight))
+    pair_cap = min(max(8 * cloud["num_points"], 1 << 22), (1 << 30) - 1)
+    rs = []
+    for _ in range(depth):
+        r_ = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
+        r_.set_pair_capacity(pair_cap)
+        r_.set_timing(False)
+        rs.append(r_)
+    r = rs[0]                                  # slot 0 also serves the per-stage breakdown below
     fargs = [frame_args(ws, cloud, v, W, H) for v in views]
-    stream = torch.cuda.Stream()
-    target = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
-    host = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(depth)]
+    stream = streams[0]
+    targets = [torch.empty((H, W, 4), dtype=torch.float16, device="cuda") for _ in range(2 * depth)]
+    target = targets[0]
+    host = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2 * depth)]
     K, Wu = args.steps, max(args.warmup, 3)
 
     def frame(i, to_host=None):
-        r.prepare(stream, pc, fargs[i % len(fargs)])
+        k = i % depth
+        rs[k].prepare(streams[k], pc, fargs[i % len(fargs)])
         if to_host is None:
-            r.render(target, pc, stream=stream)
+            rs[k].render(targets[k], pc, stream=streams[k])
         else:
-            r.render_to_host(to_host, pc, stream=stream)
+            rs[k].render_to_host(to_host, pc, stream=streams[k])
 
     # ---- kernel-only: inputs resident, frame stays on the device --------------------------------
-    r.set_timing(False)
-    for i in range(Wu):
+    for i in range(depth * ((Wu + depth - 1) // depth)):
         frame(i)
     torch.cuda.synchronize()
     st0 = r.stats()
     sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for i in range(K):
-            frame(Wu + i)
-        e1.record(stream)
+    cur = torch.cuda.current_stream()
+    e0.record(cur)
+    for st_ in streams:
+        st_.wait_event(e0)
+    for i in range(K):
+        frame(Wu + i)
+    for st_ in streams:
+        cur.wait_stream(st_)
+    e1.record(cur)
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.finish()
@@ -242,28 +258,28 @@ def run_ours(args):
 
     # ---- e2e: host buffers, uniforms H2D + frame D2H inside the timed region ----------------------
     # The public API is asynchronous on the caller's stream, so a caller that wants throughput keeps
-    # two device targets and downloads frame i on a copy stream while frame i+1 is being rendered
-    # (bin/measure.rs also submits all frames and waits once, measure.rs:98-147).  Every frame still
-    # lands in pinned host memory inside the timed region.
-    targets = [target, torch.empty_like(target)]
+    # two device targets per frame slot and downloads frame i on a copy stream while later frames are being
+    # rendered (bin/measure.rs also submits all frames and waits once, measure.rs:98-147).  Every frame
+    # still lands in pinned host memory inside the timed region.
     copy_stream = torch.cuda.Stream()
-    rendered = [torch.cuda.Event(), torch.cuda.Event()]
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    nb = 2 * depth
+    rendered = [torch.cuda.Event() for _ in range(nb)]
+    copied = [torch.cuda.Event() for _ in range(nb)]
 
     def frame_e2e(i):
-        b = i & 1
-        stream.wait_event(copied[b])                       # target b is free again (its download finished)
-        r.prepare(stream, pc, fargs[i % len(fargs)])
-        r.render(targets[b], pc, stream=stream)
-        rendered[b].record(stream)
+        k, b = i % depth, i % nb                            # slot, buffer (two buffers per slot)
+        streams[k].wait_event(copied[b])                   # target b is free again (its download finished)
+        rs[k].prepare(streams[k], pc, fargs[i % len(fargs)])
+        rs[k].render(targets[b], pc, stream=streams[k])
+        rendered[b].record(streams[k])
         copy_stream.wait_event(rendered[b])
         with torch.cuda.stream(copy_stream):
             host[b].copy_(targets[b], non_blocking=True)
             copied[b].record(copy_stream)
 
-    for b in (0, 1):
+    for b in range(nb):
         copied[b].record(copy_stream)
-    for i in range(Wu):
+    for i in range(nb * ((Wu + nb - 1) // nb)):
         frame_e2e(i)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -272,14 +288,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_fps = K / e2e_s
-    checksum = float(host[(Wu + K - 1) & 1][::97, ::89].float().sum())
+    checksum = float(host[(Wu + K - 1) % nb][::97, ::89].float().sum())
 
     # ---- per-stage CUDA-event breakdown over the same views (timing on: 8 event records per frame)
     r.set_timing(True)
     acc = {}
     counts = {"V": [], "P": []}
     for i in range(K):
-        frame(Wu + i)
+        r.prepare(stream, pc, fargs[(Wu + i) % len(fargs)])
+        r.render(target, pc, stream=stream)
         s = r.stats()
         for k_ in ("ms_preprocess", "ms_sort", "ms_blend", "ms_depth_sort", "ms_binning", "ms_tile_sort", "ms_ranges",
                    "bytes_preprocess", "bytes_sort", "bytes_blend"):
@@ -345,8 +362,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, cloud, W, H), "target_format": "rgba16float",
                    "l2": "inputs (%.0f MB cloud) larger than the 126 MB L2; no flush needed" % ((cloud["gaussians"].nbytes + cloud["sh_coefs"].nbytes) / 1e6),
-                   "N": N, "V_mean": V, "P_mean": P, "tiles": T},
-        "ms_per_frame": {"preprocess": acc["ms_preprocess"], "sort": acc["ms_sort"], "blend": acc["ms_blend"],
+                   "frames_in_flight": depth, "N": N, "V_mean": V, "P_mean": P, "tiles": T},
+        "ms_per_frame": {"note": "one frame at a time on one stream (CUDA events between the stages)", "preprocess": acc["ms_preprocess"], "sort": acc["ms_sort"], "blend": acc["ms_blend"],
                          "depth_sort": acc["ms_depth_sort"], "binning": acc["ms_binning"],
                          "tile_sort": acc["ms_tile_sort"]},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
@@ -368,6 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=2, help="multi-GPU arm: sharded frames in flight per GPU (one renderer + stream each)")
+    ap.add_argument("--equal-bands", action="store_true", help="multi-GPU arm: keep the equal tile-row split instead of cost-balanced bands")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 360 if args.impl == "ours" else 10    # 10 orbits (~1 s of GPU time) / ~2-5 s per CPU frame

@@ -42,8 +42,10 @@ def run(args):
     pc = ws.PointCloud.new(ctx, gen)
     fmt = ws.FORMAT_RGBA16_FLOAT
     N = int(cloud["num_points"])
-    sh = ws.ShardedRenderer(ws, ctx, fmt, cloud["sh_deg"], cloud["compressed"], pc, N, (W, H),
-                            pair_capacity=min(max(8 * N // world + (1 << 22), 1 << 22), (1 << 30) - 1))
+    depth = max(1, int(getattr(args, "frames_in_flight", 2)))
+    pipe = ws.ShardedPipeline(ws, ctx, fmt, cloud["sh_deg"], cloud["compressed"], pc, N, (W, H), depth=depth,
+                              pair_capacity=min(max(8 * N // world + (1 << 22), 1 << 22), (1 << 30) - 1))
+    sh = pipe.slots[0]                       # slot 0 also serves the single-frame breakdowns below
     fargs = [bench.frame_args(ws, cloud, v, W, H) for v in views]
     K, Wu = args.steps, max(args.warmup, 3)
     host = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2)] if rank == 0 else None
@@ -57,16 +59,30 @@ def run(args):
     sh.r.set_timing(False)
     # the bands are stored straight into rank 0's assembled frame (peer memory) by the compositor
     for i in range(Wu):
-        sh.frame_peer(fargs[i % len(fargs)])
+        pipe.frame_peer(fargs[i % len(fargs)])
     sync_all()
+    # cost-balanced bands from the pair counts of the warm-up frames (every rank derives the same boundaries)
+    bands0 = list(pipe.bands)
+    if not getattr(args, "equal_bands", False):
+        for _ in range(2):
+            pipe.rebalance()
+            sync_all()
+            for i in range(depth):
+                pipe.frame_peer(fargs[(Wu + i) % len(fargs)])
+            sync_all()
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    cur = torch.cuda.current_stream()
+    e0.record(cur)
+    for st in pipe.streams:
+        st.wait_event(e0)
     for i in range(K):
-        sh.frame_peer(fargs[(Wu + i) % len(fargs)])
-    e1.record()
+        pipe.frame_peer(fargs[(Wu + i) % len(fargs)])
+    for st in pipe.streams:
+        cur.wait_stream(st)
+    e1.record(cur)
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -75,12 +91,14 @@ def run(args):
 
     # ---- e2e: rank 0 additionally downloads every frame into pinned host memory -------------------
     copy_stream = torch.cuda.Stream() if rank == 0 else None     # root: download frame f while frame f+1 is produced
-    for i in range(Wu):
-        sh.frame_peer(fargs[i % len(fargs)], host=host[i & 1] if rank == 0 else None, copy_stream=copy_stream)
+    host = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2 * depth)] if rank == 0 else None
+    pipe._i = 0                               # frame i -> slot i % depth, host buffer i % (2 * depth)
+    for i in range(2 * depth * ((Wu + 2 * depth - 1) // (2 * depth))):
+        pipe.frame_peer(fargs[i % len(fargs)], host=host[i % (2 * depth)] if rank == 0 else None, copy_stream=copy_stream)
     sync_all()
     t0 = time.perf_counter()
     for i in range(K):
-        sh.frame_peer(fargs[(Wu + i) % len(fargs)], host=host[i & 1] if rank == 0 else None, copy_stream=copy_stream)
+        pipe.frame_peer(fargs[(Wu + i) % len(fargs)], host=host[i % (2 * depth)] if rank == 0 else None, copy_stream=copy_stream)
     sync_all()
     e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
@@ -122,6 +140,7 @@ def run(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": bench.workload_name(args.workload, cloud, W, H), "target_format": "rgba16float",
                        "parallelism": "stage 1 sharded by Gaussian index, stages 2-3 by tile-row band; splats, count rows, barriers and the finished bands all move by peer-memory stores (no NCCL call inside a frame)",
+                       "frames_in_flight": depth, "bands_tile_rows": list(pipe.bands), "bands_equal_split": bands0,
                        "l2": "inputs larger than L2; no flush needed", "N": N, "V_received_sum": V_sum, "P_sum": P_sum, "tiles": T},
             "ms_per_frame": {"preprocess+exchange": stage["preprocess"], "sort": stage["sort"], "blend": stage["blend"],
                              "depth_sort": stage["depth_sort"], "binning": stage["binning"], "tile_sort": stage["tile_sort"],
@@ -131,7 +150,7 @@ def run(args):
                          "traffic": None, "peak_source": peak_src + " x n_gpus"},
             "cpu_baseline": None,
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 448 * world, "d2h_bytes_per_step": W * H * 8},
-            "gpu_launches": K * world * 17,     # per rank and frame: 3 stage-1 + 3 routing + 3 finish/histogram + 6 onesweep + 3 binning + 1 composite
+            "gpu_launches": K * world * (17 + (2 if depth > 1 else 0)),     # per rank and frame: 3 stage-1 + 3 routing (+2 gates) + 1 finish/histogram + 6 onesweep + 3 binning + 1 composite
             "clocks": clocks,
         }
         sys.stdout.flush()

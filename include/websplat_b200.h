@@ -320,6 +320,14 @@ WS_API ws_status ws_renderer_shard_frame(const ws_renderer *r, void **device_ptr
  * produced; the root must not start frame f+2 before that download has finished (stream/event ordering). */
 WS_API ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
                                                  uint32_t root, const double clear[4], void *cuda_stream);
+/* Cost-balanced bands: replace the equal tile-row split of ws_renderer_shard_configure.  band_y0 has world + 1
+ * entries, 0 = band_y0[0] < ... < band_y0[world] = ceil(height / 16); rank d owns tile rows
+ * [band_y0[d], band_y0[d+1]).  Every rank must pass the same array, between frames. */
+WS_API ws_status ws_renderer_shard_set_bands(ws_renderer *r, const uint32_t *band_y0, uint32_t count);
+WS_API ws_status ws_renderer_shard_get_bands(const ws_renderer *r, uint32_t *band_y0, uint32_t count);
+/* Several sharded frames in flight per GPU (one renderer + one stream per frame slot): the peer-flag waits of
+ * ws_renderer_shard_frame_to_root move into one-warp gate kernels so that no wide kernel ever spins. */
+WS_API ws_status ws_renderer_shard_set_gated(ws_renderer *r, int32_t enabled);
 WS_API ws_status ws_renderer_shard_download(ws_renderer *r, void *dst_rgba_host, void *cuda_stream);
 
 /* ---- uniforms, for inspection (renderer.rs:125, 285) ------------------------

@@ -60,6 +60,31 @@ def main():
                 ok = ok and same3
                 print("   peer-mailbox identical=%s" % same3, flush=True)
             dist.barrier()
+        # two frames in flight (gate kernels) over cost-balanced bands: still bit-identical, for several views in a row
+        pipe = ws.ShardedPipeline(ws, ctx, fmt, 3, False, pc, n, (W, H), depth=2)
+        views = [ws.synth.orbit_camera(az) for az in (10.0, 130.0, 200.0, 340.0)]
+        vargs = [make_args(ws, cloud, p_, r_, W, H, fovx, fovy) for p_, r_ in views]
+        for round_ in range(2):
+            hosts = [torch.zeros((H, W, 4), dtype=img.dtype).pin_memory() for _ in vargs] if rank == 0 else [None] * len(vargs)
+            for a_, h_ in zip(vargs, hosts):
+                pipe.frame_peer(a_, clear=(0.1, 0.2, 0.3, 0.5), root=0, host=h_)
+            pipe.synchronize()
+            torch.cuda.synchronize()
+            if rank == 0:
+                full = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+                plain = ws.GaussianRenderer.new(ctx, fmt, 3, False)
+                for a_, h_ in zip(vargs, hosts):
+                    plain.prepare(None, full, a_)
+                    ref = torch.empty((H, W, 4), dtype=img.dtype, device="cuda")
+                    plain.render(ref, full, (0.1, 0.2, 0.3, 0.5))
+                    torch.cuda.synchronize()
+                    same4 = torch.equal(h_, ref.cpu())
+                    ok = ok and same4
+                print("   pipeline depth 2, bands %s identical=%s" % (pipe.bands, ok), flush=True)
+            dist.barrier()
+            new = pipe.rebalance()                       # second round runs on the re-cut bands
+            assert new == pipe.slots[1].bands
+        dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag.item()) == 1:

@@ -83,3 +83,29 @@ def test_count_matrix_and_offsets_gloo(ws, orc, tmp_path):
     for d in range(world):
         want = int(((rects[:, 3] >= rects[:, 1]) & (rects[:, 1] < bands[d + 1]) & (rects[:, 3] + 1 > bands[d])).sum())
         assert m0[:, d].sum() == want
+
+
+def test_balanced_bands_properties(ws):
+    """cost-balanced tile-row bands (distributed.balanced_bands): partition, monotone, at least one row each, better balance."""
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 4, 8):
+        for H in (600, 1080, 2160):
+            ty = (H + 15) // 16
+            rows = rng.uniform(0.2, 1.0, ty) * np.exp(-((np.arange(ty) - 0.4 * ty) / (0.3 * ty)) ** 2)     # a bump, like a real scene
+            b = ws.tile_row_bands(H, world)
+            imbalance = []
+            for _ in range(4):
+                loads = [rows[b[d]:b[d + 1]].sum() for d in range(world)]
+                imbalance.append(max(loads) / (sum(loads) / world))
+                nb = ws.balanced_bands(b, loads)
+                assert nb[0] == 0 and nb[-1] == ty and len(nb) == world + 1
+                assert all(nb[d + 1] > nb[d] for d in range(world))
+                b = nb
+            assert imbalance[-1] <= imbalance[0] + 1e-9
+            if world in (2, 4, 8):
+                assert imbalance[-1] < 1.0 + 1.5 * world / ty + 0.08          # within row granularity of perfect
+    # degenerate inputs leave the bands alone / stay valid
+    assert ws.balanced_bands([0, 5, 10], [0, 0]) == [0, 5, 10]
+    assert ws.balanced_bands([0, 1, 2], [9, 1]) == [0, 1, 2]
+    assert ws.balanced_bands([0, 2, 10], [100, 1]) == [0, 1, 10]
+    assert ws.balanced_bands([0, 8, 10], [1, 100]) == [0, 9, 10]

@@ -44,6 +44,16 @@ def test_sharded_world1_equals_plain(ws, orc, ctx):
     st = sh.stats()
     # only splats that touch at least one tile are routed, so the received count can be below V
     assert st["num_visible"] <= plain.stats()["num_visible"] and st["num_pairs"] == plain.stats()["num_pairs"]
+    # two frames in flight through the gated path (world 1: the gates wait on this rank's own flags)
+    pipe = ws.ShardedPipeline(ws, ctx, ws.FORMAT_RGBA32_FLOAT, 3, False, pc, cloud["num_points"], (W, H), depth=2)
+    hosts = [torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(4)]
+    for h in hosts:
+        pipe.frame_peer(args, host=h)
+    pipe.synchronize()
+    torch.cuda.synchronize()
+    for h in hosts:
+        assert torch.equal(h, t.cpu())
+    assert pipe.rebalance() == [0, (H + 15) // 16]
 
 
 def _gpu_count():

@@ -143,7 +143,7 @@ EXPORTED_SYMBOLS = [
     "ws_renderer_shard_configure", "ws_renderer_shard_export", "ws_renderer_shard_import", "ws_renderer_shard_begin",
     "ws_renderer_shard_exchange", "ws_renderer_shard_finish", "ws_renderer_shard_band", "ws_renderer_render_band",
     "ws_renderer_render_band_to_root", "ws_renderer_shard_frame", "ws_renderer_shard_download",
-    "ws_renderer_shard_frame_to_root",
+    "ws_renderer_shard_frame_to_root", "ws_renderer_shard_set_bands", "ws_renderer_shard_get_bands", "ws_renderer_shard_set_gated",
 ]
 
 _lib = None
@@ -221,6 +221,9 @@ def lib():
         "ws_renderer_render_band_to_root": (i32, [vp, vp, u32, C.POINTER(C.c_double * 4), vp]),
         "ws_renderer_shard_frame": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "ws_renderer_shard_download": (i32, [vp, vp, vp]),
+        "ws_renderer_shard_set_bands": (i32, [vp, C.POINTER(u32), u32]),
+        "ws_renderer_shard_get_bands": (i32, [vp, C.POINTER(u32), u32]),
+        "ws_renderer_shard_set_gated": (i32, [vp, i32]),
         "ws_renderer_shard_frame_to_root": (i32, [vp, vp, C.POINTER(ws_splatting_args), u32, C.POINTER(C.c_double * 4), vp]),
     }
     for name, (res, args) in sig.items():
@@ -723,4 +726,4 @@ def sort_pairs_host(ctx, keys, payload, key_bits=32):
 
 from . import scene, synth  # noqa: E402,F401
 from .scene import Scene, SceneCamera  # noqa: E402,F401
-from .distributed import ShardedRenderer, shard_cloud, tile_row_bands  # noqa: E402,F401
+from .distributed import ShardedPipeline, ShardedRenderer, balanced_bands, shard_cloud, tile_row_bands  # noqa: E402,F401

@@ -647,6 +647,7 @@ enum { TK_PRE = 0, TK_BIN = 1, TK_DSORT = 2, TK_TSORT = 6 };
 struct ShardState {
     uint32_t rank = 0, world = 0;              // world == 0: not sharded
     uint32_t width = 0, height = 0;
+    uint32_t gated = 0;                        // several sharded frames in flight: flag waits in one-warp gate kernels
     uint32_t band_y0[9] = {};                  // tile-row bands: rank d owns rows [band_y0[d], band_y0[d+1])
     uint32_t recv_cap = 0, local_cap = 0;
     uint32_t *l_splats = nullptr, *l_keys = nullptr, *l_vals = nullptr; uint2 *l_rects = nullptr;   // stage-1 output of the local shard
@@ -1118,11 +1119,44 @@ extern "C" ws_status ws_renderer_shard_import(ws_renderer *r, const void *all_ha
     return WS_OK;
 }
 
+// Custom tile-row bands (cost-balanced partition of stages 2-3): band_y0[d] .. band_y0[d+1] are the tile rows of
+// rank d.  Every rank must set the same boundaries, between frames.
+extern "C" ws_status ws_renderer_shard_set_bands(ws_renderer *r, const uint32_t *band_y0, uint32_t count)
+{
+    if (!r || !band_y0) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    ShardState &s = r->shard;
+    if (s.world < 1) return fail(WS_ERR_INVALID_ARGUMENT, "call ws_renderer_shard_configure first");
+    const uint32_t ty = (s.height + TILE - 1) / TILE;
+    if (count != s.world + 1 || band_y0[0] != 0 || band_y0[s.world] != ty) return fail(WS_ERR_INVALID_ARGUMENT, "need world + 1 boundaries from 0 to the number of tile rows");
+    for (uint32_t d = 0; d < s.world; d++)
+        if (band_y0[d + 1] <= band_y0[d]) return fail(WS_ERR_INVALID_ARGUMENT, "every rank needs at least one tile row");
+    for (uint32_t d = 0; d <= s.world; d++) s.band_y0[d] = band_y0[d];
+    return WS_OK;
+}
+
+extern "C" ws_status ws_renderer_shard_get_bands(const ws_renderer *r, uint32_t *band_y0, uint32_t count)
+{
+    if (!r || !band_y0) return fail(WS_ERR_INVALID_ARGUMENT, "NULL argument");
+    const ShardState &s = r->shard;
+    if (s.world < 1 || count != s.world + 1) return fail(WS_ERR_INVALID_ARGUMENT, "not configured / need world + 1 entries");
+    for (uint32_t d = 0; d <= s.world; d++) band_y0[d] = s.band_y0[d];
+    return WS_OK;
+}
+
+// Several sharded frames in flight on this GPU (one renderer per frame slot, one stream each): move the peer-flag
+// waits of ws_renderer_shard_frame_to_root out of the wide kernels into one-warp gate kernels.
+extern "C" ws_status ws_renderer_shard_set_gated(ws_renderer *r, int32_t enabled)
+{
+    if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
+    r->shard.gated = enabled ? 1u : 0u;
+    return WS_OK;
+}
+
 static void fill_route_args(ws_renderer *r, RouteArgs &a)
 {
     ShardState &s = r->shard;
     a.l_splats = s.l_splats; a.l_keys = s.l_keys; a.l_rects = s.l_rects; a.counters = r->d_counters;
-    a.world = s.world; a.rank = s.rank;
+    a.world = s.world; a.rank = s.rank; a.gated = s.gated;
     for (int d = 0; d < 9; d++) a.band_y0[d] = s.band_y0[d < (int)s.world + 1 ? d : s.world];
     a.part_band_counts = s.part_band_counts; a.part_band_bases = s.part_band_bases;
     a.totals = nullptr; a.matrix = nullptr;

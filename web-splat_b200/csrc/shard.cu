@@ -142,7 +142,7 @@ route_scatter_kernel(RouteArgs a)
     const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
     const uint32_t *matrix = a.matrix;
     if (a.peer_mail[a.rank]) {                    // mailbox mode: wait until every rank's count row of this frame has arrived
-        if (tid < a.world) wait_epoch(&a.peer_mail[a.rank]->flag_rows[tid], a.epoch, a.err);
+        if (!a.gated && tid < a.world) wait_epoch(&a.peer_mail[a.rank]->flag_rows[tid], a.epoch, a.err);
         __syncthreads();
         matrix = a.peer_mail[a.rank]->matrix[a.epoch & 1u];
     }
@@ -263,7 +263,7 @@ shard_finish_peer_kernel(RouteArgs a, uint32_t *vals, const uint32_t *__restrict
     const unsigned tid = threadIdx.x;
     for (unsigned i = tid; i < 4u * 256u; i += 256u) s_hist[i] = 0u;
     const ShardMailbox *mail = a.peer_mail[a.rank];
-    if (tid < a.world) wait_epoch(&mail->flag_xchg[tid], a.epoch, a.err);
+    if (!a.gated && tid < a.world) wait_epoch(&mail->flag_xchg[tid], a.epoch, a.err);
     __syncthreads();
     const uint32_t *matrix = mail->matrix[a.epoch & 1u];
     uint32_t v = 0;
@@ -285,12 +285,22 @@ __global__ void wait_bands_kernel(const ShardMailbox *mail, uint32_t world, uint
     if (threadIdx.x < world) wait_epoch(&mail->flag_band[threadIdx.x], epoch, err);
 }
 
+// Gate: ONE warp spins on a set of epoch flags; the kernel behind it in the stream starts once all have arrived.
+// Used instead of the in-kernel waits when several sharded frames are in flight on one GPU: a grid-wide spin
+// could fill every SM of this GPU while the peer it waits for is itself blocked behind this GPU's other frame
+// (a cross-GPU resource cycle); a one-warp gate cannot starve anything.
+__global__ void gate_kernel(const uint32_t *flags, uint32_t world, uint32_t epoch, uint32_t *err)
+{
+    if (threadIdx.x < world) wait_epoch(flags + threadIdx.x, epoch, err);
+}
+
 }  // namespace
 
 cudaError_t launch_shard_finish_peer(const RouteArgs &a, uint32_t *vals, const uint32_t *keys, uint32_t *hist, int passes,
                                      FrameCounters *counters, int grid, cudaStream_t stream)
 {
     // NOTE: counters->num_visible is rewritten by block 0 while other blocks of this kernel never read it
+    if (a.gated) gate_kernel<<<1, 32, 0, stream>>>(a.peer_mail[a.rank]->flag_xchg, a.world, a.epoch, a.err);
     shard_finish_peer_kernel<<<grid, 256, 0, stream>>>(a, vals, keys, hist, passes, counters);
     return cudaGetLastError();
 }
@@ -310,6 +320,7 @@ cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream
 
 cudaError_t launch_route_scatter(const RouteArgs &a, int grid, cudaStream_t stream)
 {
+    if (a.gated && a.peer_mail[a.rank]) gate_kernel<<<1, 32, 0, stream>>>(a.peer_mail[a.rank]->flag_rows, a.world, a.epoch, a.err);
     route_scatter_kernel<<<grid, RT_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }

@@ -132,6 +132,7 @@ struct RouteArgs {
     ShardMailbox *peer_mail[8];                                // NULL: NCCL mode (matrix/totals are plain buffers)
     uint32_t epoch;                                            // frame number, > 0
     uint32_t *done_counter;                                    // zeroed per frame: last-CTA detection
+    uint32_t gated;                                            // 1: flag waits run in one-warp gate kernels in front of the consumers
 };
 cudaError_t launch_shard_finish_peer(const RouteArgs &a, uint32_t *vals, const uint32_t *keys, uint32_t *hist, int passes,
                                      FrameCounters *counters, int grid, cudaStream_t stream);

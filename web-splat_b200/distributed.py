@@ -17,6 +17,35 @@ def tile_row_bands(height, world):
     return [(ty * d) // world for d in range(world + 1)]
 
 
+def balanced_bands(bands, loads, min_rows=1):
+    """Cost-balanced tile-row bands from the per-band load of the last frame(s) ("a cost-balanced
+    map using the gathered counts").  The load is taken as uniform over the rows of its band, which gives a piecewise-
+    linear cumulative cost over the tile rows; the new boundaries cut it into equal parts, rounded to whole rows with at
+    least `min_rows` rows per rank.  Pure host arithmetic on values every rank holds identically, so every rank derives
+    the same bands.  Applying it a few times converges (each round refines the density estimate)."""
+    world = len(bands) - 1
+    ty = int(bands[-1])
+    loads = [max(float(x), 0.0) for x in loads]
+    total = sum(loads)
+    if total <= 0.0 or ty < world * min_rows:
+        return [int(b) for b in bands]
+    cum = [0.0] * (ty + 1)                                  # cumulative cost at every row boundary
+    for d in range(world):
+        rows = bands[d + 1] - bands[d]
+        for y in range(bands[d], bands[d + 1]):
+            cum[y + 1] = cum[y] + loads[d] / rows
+    out = [0]
+    for d in range(1, world):
+        target = total * d / world
+        y = out[-1] + min_rows
+        hi = ty - (world - d) * min_rows                    # leave room for the ranks behind
+        while y < hi and abs(cum[y + 1] - target) <= abs(cum[y] - target):
+            y += 1
+        out.append(min(y, hi))
+    out.append(ty)
+    return out
+
+
 def shard_cloud(cloud, rank, world):
     """Gaussians [rank*N/world, (rank+1)*N/world) of a cloud dict, keeping the GLOBAL bbox / centre
     (clip box, scene centre and extent come from them: renderer.rs:622-651)."""
@@ -83,6 +112,39 @@ class ShardedRenderer:
         self.frame_out = torch.zeros((self.H, self.W, 4), dtype=dt, device=dev)
         self._frames = 1                                         # mirrors the library's epoch (first frame = 1)
         self._copied = [None, None]
+
+    def set_bands(self, bands):
+        """Install custom tile-row bands (same list on every rank, no frame in flight)."""
+        torch, ws = self.torch, self.ws
+        arr = (C.c_uint32 * (self.world + 1))(*[int(b) for b in bands])
+        ws._check(ws.lib().ws_renderer_shard_set_bands(self.r._h, arr, self.world + 1))
+        self.bands = [int(b) for b in bands]
+        first, rows = C.c_uint32(), C.c_uint32()
+        ws._check(ws.lib().ws_renderer_shard_band(self.r._h, C.byref(first), C.byref(rows)))
+        self.first_row, self.num_rows = first.value, rows.value
+        max_rows = max(min(self.bands[d + 1] * 16, self.H) - min(self.bands[d] * 16, self.H) for d in range(self.world))
+        if max_rows != self.max_rows:                            # buffers of the all-gather variant
+            self.max_rows = max_rows
+            self.band = torch.zeros((max_rows, self.W, 4), dtype=self.band.dtype, device=self.band.device)
+            self.gathered = torch.zeros((self.world, max_rows, self.W, 4), dtype=self.band.dtype, device=self.band.device)
+
+    def band_loads(self):
+        """Pairs each rank produced in its band in the last frame (all ranks get the same list)."""
+        torch, dist = self.torch, self.dist
+        torch.cuda.synchronize()
+        mine = torch.tensor([float(self.r.stats(allow_overflow=True)["num_pairs"])], dtype=torch.float64, device="cuda")
+        if self.world == 1:
+            return [float(mine.item())]
+        allv = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allv, mine, group=self.group)
+        return [float(v.item()) for v in allv]
+
+    def rebalance(self):
+        """Re-cut the bands from the last frame's per-band pair counts; returns the new bands."""
+        new = balanced_bands(self.bands, self.band_loads())
+        if new != self.bands:
+            self.set_bands(new)
+        return new
 
     def frame(self, args, clear=(0.0, 0.0, 0.0, 0.0), gather=True, marks=None):
         """Enqueue one frame on torch's current stream; returns the assembled frame (device tensor).
@@ -208,3 +270,49 @@ class ShardedRenderer:
 
     def stats(self, allow_overflow=False):
         return self.r.stats(allow_overflow)
+
+
+class ShardedPipeline:
+    """`depth` sharded frames in flight per GPU: one ShardedRenderer (own scratch, mailboxes, peer mappings, frame
+    buffers) and one CUDA stream per frame slot, all sharing the resident point-cloud shard.  Frame i runs in slot
+    i % depth; every rank must submit the same frames in the same order.  At small per-GPU shares the kernels of one
+    frame are latency-bound and leave most SMs idle; a second frame fills them (and the waits on peer flags).  With
+    depth > 1 the flag waits run in one-warp gate kernels (ws_renderer_shard_set_gated) so that two frames can never
+    starve each other across GPUs."""
+
+    def __init__(self, ws, ctx, color_format, sh_deg, compressed, pc, total_points, viewport, depth=2, group=None,
+                 pair_capacity=None):
+        import torch
+        self.torch, self.ws, self.depth = torch, ws, int(depth)
+        self.slots = [ShardedRenderer(ws, ctx, color_format, sh_deg, compressed, pc, total_points, viewport, group, pair_capacity)
+                      for _ in range(self.depth)]
+        self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
+        self.rank, self.world = self.slots[0].rank, self.slots[0].world
+        for s in self.slots:
+            s.r.set_timing(False)
+            ws._check(ws.lib().ws_renderer_shard_set_gated(s.r._h, 1 if self.depth > 1 else 0))
+        self._i = 0
+
+    def frame_peer(self, args, clear=(0.0, 0.0, 0.0, 0.0), root=0, host=None, copy_stream=None):
+        k = self._i % self.depth
+        self._i += 1
+        with self.torch.cuda.stream(self.streams[k]):
+            self.slots[k].frame_peer(args, clear, root, host, copy_stream)
+        return k
+
+    def synchronize(self):
+        for st in self.streams:
+            st.synchronize()
+
+    @property
+    def bands(self):
+        return self.slots[0].bands
+
+    def rebalance(self):
+        """Balance from slot 0's last frame and install the same bands in every slot."""
+        self.synchronize()
+        new = balanced_bands(self.slots[0].bands, self.slots[0].band_loads())
+        for s in self.slots:
+            if new != s.bands:
+                s.set_bands(new)
+        return new
