@@ -28,14 +28,29 @@ def run(args):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # one process generates the cloud, the others load it (identical bytes on every rank)
-    if local == 0:
-        cloud, W, H, views = bench.make_workload(args.workload)
-    dist.barrier()
-    if local != 0:
-        cloud, W, H, views = bench.make_workload(args.workload)
+    if args.workload == "cfg5":
+        # 24 M Gaussians: every rank generates ONLY its own eighth (seeded by rank) -- the union is the cloud; the
+        # global bbox / centre the frame needs are reduced over the ranks.  (cfg5 exists only sharded, so there is
+        # no single-GPU frame to stay byte-identical with.)
+        n_all, W, H, seed, _ = ws.synth.CONFIGS["cfg5"]
+        lo_i, hi_i = (n_all * rank) // world, (n_all * (rank + 1)) // world
+        shard = ws.synth.make_cloud(hi_i - lo_i, seed + 7919 * rank, density_n=n_all)
+        lo = torch.tensor(shard["aabb_min"], device="cuda"); hi = torch.tensor(shard["aabb_max"], device="cuda")
+        csum = torch.tensor(shard["center"].astype(np.float64) * (hi_i - lo_i), device="cuda")
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(csum)
+        cloud = dict(shard, num_points=n_all, aabb_min=lo.cpu().numpy(), aabb_max=hi.cpu().numpy(),
+                     center=(csum / n_all).cpu().numpy().astype(np.float32))
+        shard = dict(shard, aabb_min=cloud["aabb_min"], aabb_max=cloud["aabb_max"], center=cloud["center"])
+        views = ws.synth.orbit_views(36)
+    else:
+        # one process generates the cloud, the others load it (identical bytes on every rank)
+        if local == 0:
+            cloud, W, H, views = bench.make_workload(args.workload)
+        dist.barrier()
+        if local != 0:
+            cloud, W, H, views = bench.make_workload(args.workload)
+        shard = ws.shard_cloud(cloud, rank, world)
     ctx = ws.Context(local)
-    shard = ws.shard_cloud(cloud, rank, world)
     gen = ws.GenericGaussianPointCloud(shard["gaussians"], shard["sh_coefs"], shard["sh_deg"], shard["num_points"],
                                        ws.Aabb(cloud["aabb_min"], cloud["aabb_max"]), cloud["center"],
                                        compressed=cloud["compressed"], covars=cloud.get("covars"), quantization=cloud.get("quantization"))

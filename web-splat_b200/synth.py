@@ -49,10 +49,10 @@ def build_cov(rot_wxyz, scale):
     return np.stack([M[:, 0, 0], M[:, 0, 1], M[:, 0, 2], M[:, 1, 1], M[:, 1, 2], M[:, 2, 2]], axis=1).astype(np.float32)
 
 
-def _attributes(n, seed, chunk=None):
+def _attributes(n, seed, chunk=None, density_n=None):
     rng = np.random.default_rng(seed)
     xyz = rng.uniform(-1.0, 1.0, size=(n, 3)).astype(np.float32)
-    s0 = 0.6 * max(n, 1) ** (-1.0 / 3.0)
+    s0 = 0.6 * max(density_n or n, 1) ** (-1.0 / 3.0)        # splat size follows the density of the WHOLE cloud
     scale = (s0 * np.exp(0.6 * rng.standard_normal((n, 3)))).astype(np.float32)
     q = rng.standard_normal((n, 4)).astype(np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)
@@ -74,9 +74,10 @@ def _bbox_center(xyz, compressed):
     return lo.astype(np.float32), hi.astype(np.float32), center
 
 
-def make_cloud(n, seed, sh_deg=3):
-    """Raw layout (28-B Gaussian + 96-B SH).  Returns a dict of numpy buffers + metadata."""
-    xyz, scale, q, opacity, sh = _attributes(n, seed)
+def make_cloud(n, seed, sh_deg=3, density_n=None):
+    """Raw layout (28-B Gaussian + 96-B SH).  Returns a dict of numpy buffers + metadata.
+    `density_n`: total size of the cloud this one is a part of (a shard generated on its own keeps the splat size of the whole)."""
+    xyz, scale, q, opacity, sh = _attributes(n, seed, density_n=density_n)
     g = np.zeros(n, dtype=GAUSSIAN_DTYPE)
     g["xyz"] = xyz
     g["opacity"] = opacity.astype(np.float16)
