@@ -209,7 +209,7 @@ def run_ours(args):
     # `depth` frames in flight: one renderer (own scratch) + one stream + one target per frame slot, all reading the
     # same resident cloud; frame i runs in slot i % depth.  At the small configurations one frame's kernels are
     # latency-bound and a second frame fills the idle SMs (cfg1 +36 %, cfg2 +22 %, cfg3 +2 %: profiles/r01o_*).
-    depth = max(1, int(args.frames_in_flight))
+    depth = int(args.frames_in_flight) if args.frames_in_flight > 0 else 2
     pair_cap = min(max(8 * cloud["num_points"], 1 << 22), (1 << 30) - 1)
     rs = []
     for _ in range(depth):
@@ -385,7 +385,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frames-in-flight", type=int, default=2, help="multi-GPU arm: sharded frames in flight per GPU (one renderer + stream each)")
+    ap.add_argument("--frames-in-flight", type=int, default=0,
+                    help="frames in flight per GPU (one renderer + stream per frame slot); 0 = auto: 2, and 3 at 8 GPUs "
+                         "(the smaller the per-GPU share, the more latency-bound a single frame is)")
     ap.add_argument("--equal-bands", action="store_true", help="multi-GPU arm: keep the equal tile-row split instead of cost-balanced bands")
     args = ap.parse_args()
     if args.steps is None:
