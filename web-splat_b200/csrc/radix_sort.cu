@@ -27,11 +27,16 @@
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
+#include <stdlib.h>
+
 namespace ws {
 
 namespace {
 
 constexpr int WARPS = SORT_THREADS / 32;
+#ifndef WS_RANK_WAYS
+#define WS_RANK_WAYS 1                         // items ranked per step; 1, 2 and 4 are built (WS_RANK_WAYS env). Measured cfg3 tile pass: 0.135 | 0.137 | 0.141 ms -- the pass is bound by shared-memory wavefronts (bank conflicts on random digits), not by the dependent chain
+#endif
 struct LbState { uint32_t excl; bool done; };
 
 // Walk one level of status words from row p down to row lo (nearest predecessor first).
@@ -67,18 +72,20 @@ __device__ __forceinline__ void lookback_level(const uint32_t *col, int p, int l
     }
 }
 
-template <bool EMIT_RANGES>
+template <bool EMIT_RANGES, int RANK_WAYS>
 __global__ void __launch_bounds__(SORT_THREADS, 3)   // 16 items x 3 CTAs/SM measured best: 8 items x 4 CTAs and 16 items x 4 CTAs (spilling) were 7-10 % slower
 onesweep_pass_kernel(SortPassArgs a)
 {
-    __shared__ uint32_t s_keys[SORT_PART];      // during ranking the first 8 KB double as the peer masks
-    __shared__ uint32_t s_vals[SORT_PART];
+    __shared__ __align__(16) uint32_t s_keys[SORT_PART];      // during ranking s_keys / s_vals double as the peer masks
+    __shared__ __align__(16) uint32_t s_vals[SORT_PART];
     __shared__ uint32_t s_whist[WARPS][256];
     __shared__ uint32_t s_binstart[256];      // first local position of each bin in the partition
     __shared__ uint32_t s_gbase[256];         // global position of local position 0, per bin
     __shared__ uint32_t s_scan[WARPS];
     __shared__ uint32_t s_part;
 
+    static_assert(SORT_ITEMS % RANK_WAYS == 0 && WARPS * RANK_WAYS * 256 <= 2 * SORT_PART, "peer masks must fit in s_keys + s_vals");
+    static_assert((WARPS * RANK_WAYS * 256) % (4 * SORT_THREADS) == 0, "mask area is cleared with one uint4 per thread and step");
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t n = *a.n_ptr;
     if (n > a.n_cap) n = a.n_cap;
@@ -126,30 +133,56 @@ onesweep_pass_kernel(SortPassArgs a)
                 key[i] = (li < nvalid) ? a.keys_in[base + li] : 0xffffffffu;   // pads rank last (radix_sort.wgsl:79)
             }
         }
+        // peer masks: RANK_WAYS x 256 words per warp, carved out of s_keys / s_vals (free until the reorder)
 #pragma unroll
-        for (int i = 0; i < WARPS; i++) { s_whist[i][tid] = 0u; s_keys[i * 256 + tid] = 0u; }
+        for (int i = 0; i < WARPS; i++) s_whist[i][tid] = 0u;
+        {
+            uint4 *zk = reinterpret_cast<uint4 *>(s_keys), *zv = reinterpret_cast<uint4 *>(s_vals);
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < (WARPS * RANK_WAYS * 256) / (4 * SORT_THREADS); i++) {
+                const unsigned w = i * SORT_THREADS + tid;              // uint4 index over the mask area
+                if (w < SORT_PART / 4u) zk[w] = z4; else zv[w - SORT_PART / 4u] = z4;
+            }
+        }
         __syncthreads();
 
-        // ---- rank inside the warp: peers via atomicOr masks, running count via the lowest peer
+        // ---- rank inside the warp.  Each lane ORs its lane bit into the peer mask of its digit (atomicOr without
+        //      return), reads the mask back, and the lowest peer advances the warp's digit counter.  RANK_WAYS items
+        //      are ranked per step with independent shared-memory chains: item j's rank adds the peer counts of the
+        //      items before it in the step for its own digit (their masks are complete after the same warp barrier).
         uint32_t rank2[SORT_ITEMS / 2];       // two 16-bit ranks per register (a rank is < 512)
         {
             uint32_t *wh = s_whist[warp];
-            uint32_t *wm = s_keys + warp * 256u;          // this warp's 256 peer masks (all zero between items)
-            const uint32_t lanebit = 1u << lane;
+            const unsigned mw = warp * (RANK_WAYS * 256u);
+            uint32_t *wm = (mw < (unsigned)SORT_PART) ? (s_keys + mw) : (s_vals + (mw - SORT_PART));
+            const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
 #pragma unroll
-            for (int i = 0; i < SORT_ITEMS; i++) {
-                const uint32_t d = (key[i] >> shift) & 255u;
-                atomicOr(&wm[d], lanebit);
-                __syncwarp();
-                const uint32_t peers = wm[d];
-                const uint32_t old = wh[d];               // same value for all peers (broadcast read)
-                __syncwarp();
-                if ((peers & (lanebit - 1u)) == 0u) {     // lowest peer: advance the counter, clear the mask
-                    wh[d] = old + (uint32_t)__popc(peers);
-                    wm[d] = 0u;
+            for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_WAYS) {
+                uint32_t d[RANK_WAYS], peers[RANK_WAYS], rk[RANK_WAYS];
+#pragma unroll
+                for (int j = 0; j < RANK_WAYS; j++) {
+                    d[j] = (key[i0 + j] >> shift) & 255u;
+                    atomicOr(&wm[j * 256 + d[j]], lanebit);
                 }
-                const uint32_t rk = old + (uint32_t)__popc(peers & (lanebit - 1u));
-                if (i & 1) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < RANK_WAYS; j++) {
+                    peers[j] = wm[j * 256 + d[j]];
+                    rk[j] = wh[d[j]] + (uint32_t)__popc(peers[j] & lower);      // counter: same value for all peers
+#pragma unroll
+                    for (int e = 0; e < j; e++) rk[j] += (uint32_t)__popc(wm[e * 256 + d[j]]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < RANK_WAYS; j++) {
+                    if ((peers[j] & lower) == 0u) {                              // lowest peer: advance the counter, clear the mask
+                        atomicAdd(&wh[d[j]], (uint32_t)__popc(peers[j]));
+                        wm[j * 256 + d[j]] = 0u;
+                    }
+                    const int i = i0 + j;
+                    if (i & 1) rank2[i >> 1] |= rk[j] << 16; else rank2[i >> 1] = rk[j];
+                }
                 __syncwarp();
             }
         }
@@ -274,20 +307,39 @@ sort_histogram_kernel(const uint32_t *__restrict__ keys, const uint32_t *n_ptr, 
 
 }  // namespace
 
+static int rank_ways()
+{
+    static int ways = [] {
+        const char *e = getenv("WS_RANK_WAYS");              // tuning knob for profiles/; the default is what ships
+        const int w = e ? atoi(e) : WS_RANK_WAYS;
+        return (w == 1 || w == 2 || w == 4) ? w : WS_RANK_WAYS;
+    }();
+    return ways;
+}
+
 cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t stream)
 {
-    if (a.ranges) onesweep_pass_kernel<true><<<grid, SORT_THREADS, 0, stream>>>(a);
-    else onesweep_pass_kernel<false><<<grid, SORT_THREADS, 0, stream>>>(a);
+    const int w = rank_ways();
+#define WS_LAUNCH(R, W) onesweep_pass_kernel<R, W><<<grid, SORT_THREADS, 0, stream>>>(a)
+    if (a.ranges) { if (w == 4) WS_LAUNCH(true, 4); else if (w == 2) WS_LAUNCH(true, 2); else WS_LAUNCH(true, 1); }
+    else          { if (w == 4) WS_LAUNCH(false, 4); else if (w == 2) WS_LAUNCH(false, 2); else WS_LAUNCH(false, 1); }
+#undef WS_LAUNCH
     return cudaGetLastError();
 }
 
 int sort_pass_blocks_per_sm()
 {
-    int nb = 0, nb2 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, onesweep_pass_kernel<false>, SORT_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, onesweep_pass_kernel<true>, SORT_THREADS, 0);
-    if (nb2 < nb) nb = nb2;
-    return nb > 0 ? nb : 1;
+    int best = 1 << 30;
+    auto probe = [&](auto kernel) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, SORT_THREADS, 0);
+        if (nb < best) best = nb;
+    };
+    const int w = rank_ways();
+    if (w == 4) { probe(onesweep_pass_kernel<false, 4>); probe(onesweep_pass_kernel<true, 4>); }
+    else if (w == 2) { probe(onesweep_pass_kernel<false, 2>); probe(onesweep_pass_kernel<true, 2>); }
+    else { probe(onesweep_pass_kernel<false, 1>); probe(onesweep_pass_kernel<true, 1>); }
+    return best > 0 && best < (1 << 30) ? best : 1;
 }
 
 cudaError_t launch_sort_histogram(const uint32_t *keys, const uint32_t *n_ptr, uint32_t n_cap,
