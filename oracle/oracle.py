@@ -124,7 +124,12 @@ def render_settings(cloud, gaussian_scaling=1.0, max_sh_deg=3, mip_splatting=Non
     s.max_sh_deg = max_sh_deg
     s.mip_splatting = int(mip_splatting if mip_splatting is not None else bool(pc_mip))
     s.kernel_size = kernel_size if kernel_size is not None else (pc_kernel if pc_kernel is not None else 0.3)
-    lo, hi = (cloud["aabb_min"], cloud["aabb_max"]) if clipping_box is None else clipping_box
+    if clipping_box is None:
+        lo, hi = cloud["aabb_min"], cloud["aabb_max"]
+    elif hasattr(clipping_box, "min"):                      # an Aabb-like object
+        lo, hi = clipping_box.min, clipping_box.max
+    else:
+        lo, hi = clipping_box
     for i in range(3):
         s.clip_min[i] = float(lo[i]); s.clip_max[i] = float(hi[i]); s.center[i] = float(cloud["center"][i])
     s.walltime = walltime

@@ -148,6 +148,23 @@ def test_options_mip_kernel_scaling_walltime(ws, orc, ctx):
     _check_all_stages(ws, orc, ctx, cloud, pos, rot, 400, 300, walltime=0.6)       # partially revealed: NaN axes vanish
 
 
+def test_options_clipping_box_and_background(ws, orc, ctx):
+    """§8(f) N4: an explicit clipping box (preprocess.wgsl:177) through every stage, and the `Display` pass
+    (renderer.rs:556-583: the splat frame blended PREMULTIPLIED over a target cleared with the background colour)
+    expressed as render(clear = background)."""
+    cloud = ws.synth.make_cloud(20000, 12)
+    pos, rot = ws.synth.orbit_camera(200.0)
+    box = ws.Aabb([-0.5, -1.0, -0.25], [0.75, 0.5, 1.0])
+    r, st, _ = _check_all_stages(ws, orc, ctx, cloud, pos, rot, 400, 300, clipping_box=box)
+    full = _frame(ws, ctx, cloud, pos, rot, 400, 300)[0].stats()["num_visible"]
+    assert 0 < st["num_visible"] < full
+    bg = (0.2, 0.4, 0.6, 1.0)
+    _, _, on_bg, _ = _frame(ws, ctx, cloud, pos, rot, 400, 300, clear=bg)
+    _, _, on_zero, _ = _frame(ws, ctx, cloud, pos, rot, 400, 300)
+    want = on_zero + (1.0 - on_zero[..., 3:4]) * np.asarray(bg, np.float32)        # src + dst * (1 - src.a)
+    assert np.abs(on_bg - want).max() < 2e-6
+
+
 def test_edge_cases(ws, orc, ctx):
     import torch
     pos, rot = ws.synth.fixed_camera()
