@@ -93,42 +93,9 @@ bin_count_kernel(BinningArgs a)
 __global__ void __launch_bounds__(1024)
 bin_scan_kernel(BinningArgs a)
 {
-    __shared__ uint32_t total_out;
     const uint32_t V = a.counters->num_visible;
     const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
-    const uint32_t *counts = a.part_counts;
-    uint32_t *bases = a.part_bases;
-    __shared__ uint32_t s_w[32];
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t per = (nparts + 1023u) / 1024u;            // contiguous elements per thread
-    const uint32_t lo = tid * per, hi = (lo + per < nparts) ? lo + per : nparts;
-    uint32_t sum = 0;
-#pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t v = s_w[lane];
-        uint32_t vi = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
-            if ((int)lane >= o) vi += t;
-        }
-        s_w[lane] = vi - v;                                   // exclusive offset of each warp
-        if (lane == 31) total_out = vi;
-    }
-    __syncthreads();
-    uint32_t run = s_w[warp] + incl - sum;
-#pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) { const uint32_t c = counts[i]; bases[i] = run; run += c; }
-    __syncthreads();
+    const uint32_t total_out = block_exclusive_scan_1024(a.part_counts, a.part_bases, nparts);
     if (threadIdx.x == 0) {
         const uint32_t P = (nparts > 0u) ? total_out : 0u;
         a.counters->num_pairs = P;

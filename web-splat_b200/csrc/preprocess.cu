@@ -342,23 +342,41 @@ count_kernel(PreprocessArgs a)
     const uint32_t n = U.num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
     constexpr int NDIG = 4;
-    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
-        const uint32_t idx = part * PP_THREADS + tid;
-        bool keep = false;
-        uint32_t key = 0;
-        if (idx < n) {
+    // CNT_UNROLL consecutive partitions per trip: their 3 * CNT_UNROLL loads are issued before the first use, and the
+    // block-wide counts (one barrier each) follow back to back -- a single partition per trip left the loads exposed
+    // behind every barrier (r01m: long_scoreboard 35 %, 1.9 TB/s)
+    constexpr uint32_t CNT_UNROLL = 4;
+    for (uint32_t part0 = blockIdx.x * CNT_UNROLL; part0 < nparts; part0 += gridDim.x * CNT_UNROLL) {
+        float px[CNT_UNROLL], py[CNT_UNROLL], pz[CNT_UNROLL];
+#pragma unroll
+        for (uint32_t u = 0; u < CNT_UNROLL; u++) {
+            uint32_t idx = (part0 + u) * PP_THREADS + tid;
+            idx = idx < n ? idx : n - 1u;                                  // clamped: the loads stay unconditional (n > 0 here)
             const float *p = a.xyz + (size_t)idx * 3u;
-            float cs[4], pp[4];
-            keep = cull_project<COMPRESSED>(U, __ldg(p), __ldg(p + 1), __ldg(p + 2), cs, pp);
-            key = depth_key<COMPRESSED>(U, pp[2]);
+            px[u] = __ldg(p); py[u] = __ldg(p + 1); pz[u] = __ldg(p + 2);
         }
-        const uint32_t cnt = (uint32_t)__syncthreads_count(keep ? 1 : 0);
-        if (tid == 0) a.part_counts[part] = cnt;
+        bool keep[CNT_UNROLL];
+        uint32_t key[CNT_UNROLL];
+#pragma unroll
+        for (uint32_t u = 0; u < CNT_UNROLL; u++) {
+            float cs[4], pp[4];
+            const bool valid = (part0 + u) * PP_THREADS + tid < n;
+            keep[u] = cull_project<COMPRESSED>(U, px[u], py[u], pz[u], cs, pp) && valid;
+            key[u] = depth_key<COMPRESSED>(U, pp[2]);
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < CNT_UNROLL; u++) {
+            const uint32_t cnt = (uint32_t)__syncthreads_count(keep[u] ? 1 : 0);
+            if (tid == 0 && part0 + u < nparts) a.part_counts[part0 + u] = cnt;
+        }
         // shared atomics without return sustain ~120 G warp-ops/s on B200 whatever the spread
         // (profiles/microbench/rank_primitives.cu); MATCH-aggregating them was 25x slower
-        if (keep) {
 #pragma unroll
-            for (int d = 0; d < NDIG; d++) atomicAdd(&s_hist[d * 256 + ((key >> (8 * d)) & 255u)], 1u);
+        for (uint32_t u = 0; u < CNT_UNROLL; u++) {
+            if (keep[u]) {
+#pragma unroll
+                for (int d = 0; d < NDIG; d++) atomicAdd(&s_hist[d * 256 + ((key[u] >> (8 * d)) & 255u)], 1u);
+            }
         }
     }
     __syncthreads();
@@ -373,41 +391,10 @@ __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, const FrameUniforms *uniforms,
             FrameCounters *counters)
 {
-    __shared__ uint32_t total_out;
     const uint32_t n = uniforms->num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
-    __shared__ uint32_t s_w[32];
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t per = (nparts + 1023u) / 1024u;            // contiguous elements per thread
-    const uint32_t lo = tid * per, hi = (lo + per < nparts) ? lo + per : nparts;
-    uint32_t sum = 0;
-#pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t v = s_w[lane];
-        uint32_t vi = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
-            if ((int)lane >= o) vi += t;
-        }
-        s_w[lane] = vi - v;                                   // exclusive offset of each warp
-        if (lane == 31) total_out = vi;
-    }
-    __syncthreads();
-    uint32_t run = s_w[warp] + incl - sum;
-#pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) { const uint32_t c = counts[i]; bases[i] = run; run += c; }
-    __syncthreads();
-    if (threadIdx.x == 0) counters->num_visible = total_out;
+    const uint32_t total = block_exclusive_scan_1024(counts, bases, nparts);
+    if (threadIdx.x == 0) counters->num_visible = total;
 }
 
 // ---- (3) MAIN ---------------------------------------------------------------------------------
