@@ -1,4 +1,5 @@
-"""Times the section 8(f) ingest rows: .ply / .npz file image in host memory -> resident GPU layouts,
+"""(test infrastructure: it times the CPU oracle next to the product, so it lives under tests/)
+Times the section 8(f) ingest rows: .ply / .npz file image in host memory -> resident GPU layouts,
 next to the CPU oracle's conversion of the same arrays.  Prints one JSON line per format."""
 import json
 import sys
