@@ -68,10 +68,14 @@ def test_no_cpu_fallback_without_gpu(ws):
 
 def test_product_does_not_import_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
-    pkg = os.path.join(ROOT, "web-splat_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
-                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
-                for pat in (r'#\s*include\s*[<"][^>"]*oracle', r"libws_oracle", r"^\s*from\s+oracle\b", r"^\s*import\s+oracle\b", r"wso_[a-z_]+\s*\("):
-                    assert not re.search(pat, txt, re.M), (fn, pat)
+    pats = (r'#\s*include\s*[<"][^>"]*oracle', r"libws_oracle", r"^\s*from\s+oracle\b", r"^\s*import\s+oracle\b", r"wso_[a-z_]+\s*\(")
+    roots = [os.path.join(ROOT, d) for d in ("web-splat_b200", "include", "scripts", "bindings")]
+    files = [os.path.join(ROOT, f) for f in ("bench_multi.py", "websplat_b200.py")]
+    for root in roots:
+        for dirpath, _, names in os.walk(root):
+            files += [os.path.join(dirpath, fn) for fn in names]
+    for path in files:
+        if path.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", ".rs", ".sh")):
+            txt = open(path, errors="ignore").read()
+            for pat in pats:
+                assert not re.search(pat, txt, re.M), (path, pat)
