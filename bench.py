@@ -34,7 +34,8 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "frames/sec"
-KERNELS_PER_FRAME_FIXED = 1 + 1 + 1         # preprocess, binning, composite (+ onesweep passes; tile ranges are fused into the last pass)
+KERNELS_STAGE1 = 3                          # count, scan, preprocess
+KERNELS_BINNING = 3                         # count, scan, expand (per slab; the tile ranges are fused into the last onesweep pass)
 
 
 def measured_peaks():
@@ -210,12 +211,14 @@ def run_ours(args):
     # same resident cloud; frame i runs in slot i % depth.  At the small configurations one frame's kernels are
     # latency-bound and a second frame fills the idle SMs (cfg1 +36 %, cfg2 +22 %, cfg3 +2 %: profiles/r01o_*).
     depth = int(args.frames_in_flight) if args.frames_in_flight > 0 else 2
+    split = not args.no_occlusion_split
     pair_cap = min(max(8 * cloud["num_points"], 1 << 22), (1 << 30) - 1)
     rs = []
     for _ in range(depth):
         r_ = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
         r_.set_pair_capacity(pair_cap)
         r_.set_timing(False)
+        r_.set_occlusion_split(split)
         rs.append(r_)
     r = rs[0]                                  # slot 0 also serves the per-stage breakdown below
     fargs = [frame_args(ws, cloud, v, W, H) for v in views]
@@ -369,14 +372,18 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, cloud, W, H), "target_format": "rgba16float",
                    "l2": "inputs (%.0f MB cloud) larger than the 126 MB L2; no flush needed" % ((cloud["gaussians"].nbytes + cloud["sh_coefs"].nbytes) / 1e6),
-                   "frames_in_flight": depth, "N": N, "V_mean": V, "P_mean": P, "tiles": T},
+                   "frames_in_flight": depth,
+                   "occlusion_split": ("two depth slabs, the far one culled against the tiles the near one saturated: P_mean counts "
+                                       "the pairs actually emitted; the image is bit-identical to the one-pass frame") if split else "off",
+                   "N": N, "V_mean": V, "P_mean": P, "tiles": T},
         "ms_per_frame": {"note": "one frame at a time on one stream (CUDA events between the stages)", "preprocess": acc["ms_preprocess"], "sort": acc["ms_sort"], "blend": acc["ms_blend"],
                          "depth_sort": acc["ms_depth_sort"], "binning": acc["ms_binning"],
                          "tile_sort": acc["ms_tile_sort"]},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 448, "d2h_bytes_per_step": W * H * 8,
                 "checksum": checksum},
-        "gpu_launches": K * (KERNELS_PER_FRAME_FIXED + depth_passes + tile_passes),
+        # stage 1 + depth passes + per slab (binning + tile passes + compositor); two slabs with the occlusion split
+        "gpu_launches": K * (KERNELS_STAGE1 + depth_passes + (2 if split else 1) * (KERNELS_BINNING + tile_passes + 1)),
         "clocks": clocks,
     }
     if rank == 0:
@@ -395,6 +402,7 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=0,
                     help="frames in flight per GPU (one renderer + stream per frame slot); 0 = auto: 2, and 3 at 8 GPUs "
                          "(the smaller the per-GPU share, the more latency-bound a single frame is)")
+    ap.add_argument("--no-occlusion-split", action="store_true", help="single-GPU arm: bin / tile-sort / composite all pairs in one pass")
     ap.add_argument("--equal-bands", action="store_true", help="multi-GPU arm: keep the equal tile-row split instead of cost-balanced bands")
     args = ap.parse_args()
     if args.steps is None:

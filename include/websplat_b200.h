@@ -253,6 +253,12 @@ WS_API ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled);
  * capacities) instead of 16 launches -- the frame-graph analogue of the reference recording one command
  * buffer per frame (src/lib.rs:415-500).  Default on; this switch exists for A/B measurements. */
 WS_API ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled);
+/* Occlusion split (default on, single-GPU frames): the depth-sorted splats are binned, tile-sorted and composited
+ * in two slabs, nearest half first; a splat of the far half whose tiles were all saturated by the near half emits no
+ * (tile, splat) pair.  Per pixel the blends and early-out tests are those of the one-pass frame: the image is
+ * bit-identical, while num_pairs counts only the pairs that were emitted.  Turn it off to get the complete pair list
+ * in the WS_BUF_PAIR_* / WS_BUF_TILE_RANGES read-backs (with the split they describe the far slab). */
+WS_API ws_status ws_renderer_set_occlusion_split(ws_renderer *r, int32_t enabled);
 
 /* ---- intermediate read-back (parity tests; synchronises) -------------------
  * Copies an intermediate buffer of the LAST prepared frame to host memory. */

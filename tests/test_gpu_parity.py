@@ -18,12 +18,16 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _frame(ws, ctx, cloud, pos, rot, W, H, fmt=None, clear=(0, 0, 0, 0), **kw):
+def _frame(ws, ctx, cloud, pos, rot, W, H, fmt=None, clear=(0, 0, 0, 0), split=False, **kw):
+    """One frame through the C ABI.  split=False: one binning + tile sort over all pairs, so that the pair-list
+    read-backs and num_pairs are the complete ones the oracle produces (the occlusion split, on by default in the
+    product, emits fewer pairs for the same image: test_occlusion_split_is_bit_identical)."""
     import torch
     fmt = ws.FORMAT_RGBA32_FLOAT if fmt is None else fmt
     fovx, fovy = ws.synth.fov_for_viewport(W, H)
     pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
     r = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
+    r.set_occlusion_split(split)
     args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy, **kw)
     r.prepare(None, pc, args)
     dt = {0: torch.uint8, 1: torch.float16, 2: torch.float32}[fmt]
@@ -163,6 +167,44 @@ def test_options_clipping_box_and_background(ws, orc, ctx):
     _, _, on_zero, _ = _frame(ws, ctx, cloud, pos, rot, 400, 300)
     want = on_zero + (1.0 - on_zero[..., 3:4]) * np.asarray(bg, np.float32)        # src + dst * (1 - src.a)
     assert np.abs(on_bg - want).max() < 2e-6
+
+
+def test_occlusion_split_is_bit_identical(ws, orc, ctx):
+    """Two depth slabs with saturated-tile culling of the far one: same pixels, bit for bit, from fewer pairs."""
+    cases = [(ws.synth.make_cloud(150000, 21), 320, 200, 30.0, ws.FORMAT_RGBA32_FLOAT),      # dense: most tiles saturate
+             (ws.synth.make_cloud(150000, 21), 320, 200, 200.0, ws.FORMAT_RGBA16_FLOAT),
+             (ws.synth.make_cloud(20000, 22), 800, 600, 75.0, ws.FORMAT_RGBA8_UNORM),        # sparse: few do
+             (ws.synth.make_cloud_compressed(60000, 23), 640, 360, 140.0, ws.FORMAT_RGBA32_FLOAT),
+             (ws.synth.make_cloud(5, 24), 64, 48, 0.0, ws.FORMAT_RGBA32_FLOAT),               # split point 0: empty far slab
+             (ws.synth.make_cloud(0, 25), 64, 48, 0.0, ws.FORMAT_RGBA32_FLOAT)]
+    saved = []
+    for cloud, W, H, az, fmt in cases:
+        pos, rot = ws.synth.orbit_camera(az)
+        clear = (0.1, 0.2, 0.3, 0.4)
+        r0, _, img0, _ = _frame(ws, ctx, cloud, pos, rot, W, H, fmt=fmt, clear=clear, split=False)
+        r1, _, img1, _ = _frame(ws, ctx, cloud, pos, rot, W, H, fmt=fmt, clear=clear, split=True)
+        assert np.array_equal(img0.view(np.uint8), img1.view(np.uint8))
+        s0, s1 = r0.stats(), r1.stats()
+        assert s1["num_visible"] == s0["num_visible"] and s1["num_pairs"] <= s0["num_pairs"]
+        saved.append(s1["num_pairs"] / max(s0["num_pairs"], 1))
+    assert saved[0] < 0.8, saved                         # the dense case really drops pairs
+    # a renderer can switch back and forth between frames (the CUDA graph is re-captured)
+    cloud, W, H, az, fmt = cases[0]
+    pos, rot = ws.synth.orbit_camera(az)
+    import torch
+    fovx, fovy = ws.synth.fov_for_viewport(W, H)
+    pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+    r = ws.GaussianRenderer.new(ctx, fmt, 3, False)
+    args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
+    outs = []
+    for split in (True, False, True, True):
+        r.set_occlusion_split(split)
+        r.prepare(None, pc, args)
+        t = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+        r.render(t, pc)
+        torch.cuda.synchronize()
+        outs.append(t.cpu().numpy())
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
 
 
 def test_edge_cases(ws, orc, ctx):

@@ -15,6 +15,7 @@ def test_full_size_properties(ws, orc, ctx, cfg):
     cloud = ws.synth.make_cloud(n, seed)
     pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
     r = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA16_FLOAT, 3, False)
+    r.set_occlusion_split(False)                       # the complete pair list is inspected below
     pos, rot = ws.synth.orbit_camera(40.0)
     fovx, fovy = ws.synth.fov_for_viewport(W, H)
     args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
@@ -53,6 +54,15 @@ def test_full_size_properties(ws, orc, ctx, cfg):
     img = target.cpu().numpy().astype(np.float32)
     assert np.isfinite(img).all() and img[..., 3].min() >= 0 and img[..., 3].max() <= 1.0
     t2 = torch.empty_like(target); r.render(t2, pc); torch.cuda.synchronize()
+    assert torch.equal(t2, target)
+    # the product default -- two depth slabs, the far one culled against saturated tiles -- gives the same pixels from fewer pairs
+    r.set_occlusion_split(True)
+    r.prepare(None, pc, args)
+    t3 = torch.empty_like(target); r.render(t3, pc); torch.cuda.synchronize()
+    assert torch.equal(t3, target)
+    st3 = r.stats()
+    assert st3["num_visible"] == V and st3["num_pairs"] < 0.8 * P, (st3["num_pairs"], P)
+    r.render(t2, pc); torch.cuda.synchronize()           # render() twice on a split frame: the state is not consumed
     assert torch.equal(t2, target)
     if cfg == "cfg2":
         _, order = orc.sort_pairs(okeys, np.arange(V, dtype=np.uint32))

@@ -23,6 +23,7 @@ def test_sharded_world1_equals_plain(ws, orc, ctx):
     args = make_args(ws, cloud, pos, rot, W, H, fovx, fovy)
     pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
     plain = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA32_FLOAT, 3, False)
+    plain.set_occlusion_split(False)                     # num_pairs is compared below; sharded frames never split
     plain.prepare(None, pc, args)
     t = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
     plain.render(t, pc)

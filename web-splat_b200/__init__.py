@@ -138,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "ws_aabb_center", "ws_aabb_radius", "ws_camera_fit_near_far", "ws_renderer_create", "ws_renderer_destroy",
     "ws_renderer_color_format", "ws_renderer_prepare", "ws_renderer_render", "ws_renderer_render_to_host",
     "ws_renderer_num_visible_points", "ws_renderer_stats", "ws_renderer_set_pair_capacity",
-    "ws_renderer_set_timing", "ws_renderer_set_cuda_graphs", "ws_renderer_read_buffer", "ws_sort_pairs_u32", "ws_sort_pairs_u32_host",
+    "ws_renderer_set_timing", "ws_renderer_set_cuda_graphs", "ws_renderer_set_occlusion_split", "ws_renderer_read_buffer", "ws_sort_pairs_u32", "ws_sort_pairs_u32_host",
     "ws_renderer_camera_uniform", "ws_renderer_settings_uniform", "ws_version",
     "ws_renderer_shard_configure", "ws_renderer_shard_export", "ws_renderer_shard_import", "ws_renderer_shard_begin",
     "ws_renderer_shard_exchange", "ws_renderer_shard_finish", "ws_renderer_shard_band", "ws_renderer_render_band",
@@ -205,6 +205,7 @@ def lib():
         "ws_renderer_set_pair_capacity": (i32, [vp, u64]),
         "ws_renderer_set_timing": (i32, [vp, i32]),
         "ws_renderer_set_cuda_graphs": (i32, [vp, i32]),
+        "ws_renderer_set_occlusion_split": (i32, [vp, i32]),
         "ws_renderer_read_buffer": (i32, [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "ws_sort_pairs_u32": (i32, [vp, vp, vp, u32, u32, vp]),
         "ws_sort_pairs_u32_host": (i32, [vp, vp, vp, u32, u32]),
@@ -616,6 +617,10 @@ class GaussianRenderer:
 
     def set_timing(self, enabled):
         _check(lib().ws_renderer_set_timing(self._h, int(bool(enabled))))
+
+    def set_occlusion_split(self, enabled):
+        """Two depth slabs with saturated-tile culling of the far one (default on; bit-identical image, fewer pairs)."""
+        _check(lib().ws_renderer_set_occlusion_split(self._h, int(bool(enabled))))
 
     def set_cuda_graphs(self, enabled):
         _check(lib().ws_renderer_set_cuda_graphs(self._h, int(bool(enabled))))

@@ -42,7 +42,16 @@ constexpr int BIN_NDIG = 3;
 
 struct SplatRects { uint32_t slot[BIN_SPT], xy[BIN_SPT], w[BIN_SPT], cnt[BIN_SPT]; };
 
-// slots + rectangles of the BIN_SPT consecutive depth-sorted splats of one thread
+// the range of depth-sorted positions this launch expands (ascending key = far -> near, so the near slab is the upper one);
+// the split point is a multiple of 4 so that the 16-byte slot loads stay aligned
+__device__ __forceinline__ void slab_bounds(const BinningArgs &a, uint32_t V, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t split = (V >> 1) & ~3u;
+    lo = (a.slab == 1u) ? split : 0u;
+    hi = (a.slab == 2u) ? split : V;
+}
+
+// slots + rectangles of the BIN_SPT consecutive depth-sorted splats of one thread (positions first .. first+3, below V)
 __device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first, uint32_t V, SplatRects &r)
 {
     if (first + BIN_SPT <= V) {
@@ -61,6 +70,22 @@ __device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first,
         r.w[j] = rc[j].y & 0xffffu;
         r.cnt[j] = r.w[j] * (rc[j].y >> 16);
     }
+    if (a.tile_done) {
+        // far slab: a splat all of whose tiles were saturated by the near slab cannot change a pixel.  Only small
+        // rectangles are tested (they are almost all of them); a pair emitted for a saturated tile is harmless,
+        // the compositor skips that tile.
+        const uint32_t tiles_x = a.uniforms->tiles_x;
+#pragma unroll
+        for (int j = 0; j < BIN_SPT; j++) {
+            if (r.cnt[j] > 0u && r.cnt[j] <= 16u) {
+                const uint32_t x0 = r.xy[j] & 0xffffu, y0 = r.xy[j] >> 16, h = rc[j].y >> 16;
+                bool all = true;
+                for (uint32_t yy = 0; yy < h; yy++)
+                    for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (a.tile_done[(y0 + yy) * tiles_x + x0 + xx] != 0);
+                if (all) r.cnt[j] = 0u;
+            }
+        }
+    }
 }
 
 // ---- (1) COUNT ---------------------------------------------------------------------------------
@@ -70,10 +95,12 @@ bin_count_kernel(BinningArgs a)
     __shared__ uint32_t s_red[BIN_WARPS];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
+    uint32_t lo, hi;
+    slab_bounds(a, V, lo, hi);
+    const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         SplatRects r;
-        load_rects(a, part * BIN_PART + tid * BIN_SPT, V, r);
+        load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r);
         uint32_t c = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -94,12 +121,14 @@ __global__ void __launch_bounds__(1024)
 bin_scan_kernel(BinningArgs a)
 {
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
+    uint32_t lo, hi;
+    slab_bounds(a, V, lo, hi);
+    const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
     const uint32_t total_out = block_exclusive_scan_1024(a.part_counts, a.part_bases, nparts);
     if (threadIdx.x == 0) {
         const uint32_t P = (nparts > 0u) ? total_out : 0u;
-        a.counters->num_pairs = P;
-        a.counters->pair_overflow = (P > a.uniforms->pair_capacity) ? 1u : 0u;
+        *a.num_pairs_out = P;
+        if (P > a.pair_cap) a.counters->pair_overflow = 1u;            // zeroed per frame; either slab may set it
     }
 }
 
@@ -116,9 +145,11 @@ bin_expand_kernel(BinningArgs a)
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
-    const uint32_t nparts = (V + BIN_PART - 1u) / BIN_PART;
+    uint32_t lo, hi;
+    slab_bounds(a, V, lo, hi);
+    const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
     const uint32_t tiles_x = a.uniforms->tiles_x;
-    const uint32_t cap = a.uniforms->pair_capacity;
+    const uint32_t cap = a.pair_cap;
     const uint32_t ntiles = tiles_x * a.uniforms->tiles_y;
     const int ndig = (ntiles > 65536u) ? 3 : ((ntiles > 256u) ? 2 : 1);
 
@@ -127,7 +158,7 @@ bin_expand_kernel(BinningArgs a)
 
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         SplatRects r;
-        load_rects(a, part * BIN_PART + tid * BIN_SPT, V, r);
+        load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r);
         const uint32_t base = __ldg(a.part_bases + part);
         const uint32_t mine = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
         // block scan of the per-thread totals

@@ -641,8 +641,8 @@ extern "C" int32_t ws_pointcloud_dilation_kernel_size(const ws_pointcloud *pc, f
 }
 
 // ------------------------------------------------------------------------------------
-enum { EV_START = 0, EV_PRE, EV_DSORT, EV_BIN, EV_TSORT, EV_BLEND0, EV_BLEND1, EV_COUNT };
-enum { TK_PRE = 0, TK_BIN = 1, TK_DSORT = 2, TK_TSORT = 6 };
+enum { EV_START = 0, EV_PRE, EV_DSORT, EV_BIN, EV_TSORT, EV_BLEND0, EV_BLEND1, EV_NEAR_BLEND, EV_BIN2, EV_TSORT2, EV_COUNT };
+enum { TK_PRE = 0, TK_BIN = 1, TK_DSORT = 2, TK_TSORT = 6, TK_TSORT_FAR = 9 };
 
 struct ShardState {
     uint32_t rank = 0, world = 0;              // world == 0: not sharded
@@ -707,9 +707,15 @@ struct ws_renderer {
     ShardState shard;
     // CUDA graph of one prepare() (clears + 14 kernels), replayed while (cloud, viewport, capacities) stay the same
     bool use_graphs = true;
+    // occlusion split (two depth slabs, nearest first)
+    bool split = true;                     // requested (ws_renderer_set_occlusion_split)
+    bool frame_split = false;              // the prepared frame was built split
+    float4 *d_state = nullptr; size_t state_px = 0;   // per pixel {r, g, b, T} after the near slab
+    uint8_t *d_tile_done = nullptr;        // per tile: saturated by the near slab
+    int tile_out_far = 0;
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t prep_exec = nullptr;
-    struct { const ws_pointcloud *pc; const void *gaussians, *scratch; uint32_t n, W, H, pair_cap, n_cap; } prep_key = {};
+    struct { const ws_pointcloud *pc; const void *gaussians, *scratch, *state; uint32_t n, W, H, pair_cap, n_cap; bool split; } prep_key = {};
 };
 
 static void free_shard(ws_renderer *r);
@@ -733,7 +739,7 @@ extern "C" void ws_renderer_destroy(ws_renderer *r)
     cudaSetDevice(r->ctx->device);
     free_shard(r);
     free_sort_stuff(r);
-    cudaFree(r->d_uniforms); cudaFree(r->d_ranges); cudaFree(r->d_frame);
+    cudaFree(r->d_uniforms); cudaFree(r->d_ranges); cudaFree(r->d_frame); cudaFree(r->d_state); cudaFree(r->d_tile_done);
     if (r->ev_ok) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(r->ev[i]);
     if (r->prep_exec) cudaGraphExecDestroy(r->prep_exec);
     if (r->cap_stream) cudaStreamDestroy(r->cap_stream);
@@ -790,6 +796,15 @@ extern "C" ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled
     return WS_OK;
 }
 
+// Occlusion split on/off (default on; the sharded paths never split).  Off = one binning + tile sort over all P pairs,
+// which is what the pair-list read-backs (WS_BUF_PAIR_*, WS_BUF_TILE_RANGES) and num_pairs describe exactly.
+extern "C" ws_status ws_renderer_set_occlusion_split(ws_renderer *r, int32_t enabled)
+{
+    if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
+    r->split = enabled != 0;
+    return WS_OK;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // GPURSSorter::create_sort_stuff analogue (gpu_rs.rs:141-175, renderer.rs:200-211)
@@ -812,7 +827,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         size_t off = 0;
         const size_t o_counters = off; off = align_up(off + sizeof(FrameCounters), 256);
         const size_t o_hd = off; off = align_up(off + 4 * 256 * 4, 256);
-        const size_t o_ht = off; off = align_up(off + 4 * 256 * 4, 256);
+        const size_t o_ht = off; off = align_up(off + 8 * 256 * 4, 256);      // 4 x 256 per slab
         const size_t o_sp = off; off = align_up(off + parts256 * 4, 256);
         const size_t o_sb = off; off = align_up(off + parts256 * 4, 256);
         const size_t o_pb = off; off = align_up(off + parts256 * 4, 256);
@@ -847,7 +862,9 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
     }
     if (!r->d_ranges || r->tiles_cap < tiles) {
         cudaFree(r->d_ranges); r->d_ranges = nullptr;
-        CU(cudaMalloc(&r->d_ranges, (size_t)(tiles ? tiles : 1) * 8));
+        CU(cudaMalloc(&r->d_ranges, (size_t)(tiles ? tiles : 1) * 8 * 2));      // [tiles] near / only, [tiles] far slab
+        cudaFree(r->d_tile_done); r->d_tile_done = nullptr;
+        CU(cudaMalloc(&r->d_tile_done, tiles ? tiles : 1));
         r->tiles_cap = tiles;
     }
     return WS_OK;
@@ -935,36 +952,61 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
         r->depth_out = src;
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_DSORT], stream));
-    {   // ---- stage 2b: expand into (tile, slot) pairs in depth order
-        BinningArgs a;
-        a.sorted_slots = r->d_vals[r->depth_out]; a.rects = r->d_rects; a.uniforms = r->d_uniforms;
-        a.counters = r->d_counters; a.pair_tiles = r->d_ptiles[0]; a.pair_slots = r->d_pslots[0];
-        a.part_counts = r->d_scan_bin; a.part_bases = r->d_bin_bases; a.hist = r->d_hist_tile;
-        CU(launch_binning(a, r->ctx->sm_count * 8, r->grid_bin, stream));
-    }
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_BIN], stream));
-    {   // ---- stage 2c: tile-id passes on the P pairs
+    // ---- stage 2b + 2c for one slab of the depth-sorted splats: expand into (tile, slot) pairs in depth order, then the
+    //      tile-id passes on those pairs.  `half` selects the slab's private half of the look-back status words, digit
+    //      histograms, tickets and tile ranges (the pair buffers themselves are reused: the slabs run back to back).
+    auto bin_and_tile_sort = [&](uint32_t slab, int half, int ev_bin, int ev_tsort, int *tile_out) -> ws_status {
         const size_t sparts_p = ((size_t)r->pair_cap + SORT_PART - 1) / SORT_PART;
+        const size_t gparts_p = (sparts_p + SORT_LB_GROUP - 1) / SORT_LB_GROUP;
+        // split frames give each slab half of the status words, hence half of the pair capacity (whole look-back groups)
+        const size_t part_off = half ? (sparts_p / 2 / SORT_LB_GROUP) * SORT_LB_GROUP : 0;
+        const uint32_t cap = (slab == 0u) ? r->pair_cap : (uint32_t)(((sparts_p / 2 / SORT_LB_GROUP) * SORT_LB_GROUP) * SORT_PART);
+        uint32_t *num_pairs = (slab == 1u) ? &r->d_counters->num_pairs_near : &r->d_counters->num_pairs;
+        {
+            BinningArgs a;
+            a.sorted_slots = r->d_vals[r->depth_out]; a.rects = r->d_rects; a.uniforms = r->d_uniforms;
+            a.counters = r->d_counters; a.pair_tiles = r->d_ptiles[0]; a.pair_slots = r->d_pslots[0];
+            a.part_counts = r->d_scan_bin; a.part_bases = r->d_bin_bases; a.hist = r->d_hist_tile + half * 4 * 256;
+            a.slab = slab; a.tile_done = (slab == 2u) ? r->d_tile_done : nullptr; a.pair_cap = cap; a.num_pairs_out = num_pairs;
+            CU(launch_binning(a, r->ctx->sm_count * 8, r->grid_bin, stream));
+        }
+        if (r->timing) CU(cudaEventRecord(r->ev[ev_bin], stream));
         int src = 0;
         for (int p = 0; p < r->tile_passes; p++) {
             SortPassArgs a;
             a.keys_in = r->d_ptiles[src]; a.vals_in = r->d_pslots[src];
             a.keys_out = r->d_ptiles[src ^ 1]; a.vals_out = r->d_pslots[src ^ 1];
-            a.n_ptr = &r->d_counters->num_pairs; a.n_cap = r->pair_cap;
-            a.status = r->d_status_tile + (size_t)p * sparts_p * 256;
-            a.gstatus = r->d_gstatus_tile + (size_t)p * ((sparts_p + SORT_LB_GROUP - 1) / SORT_LB_GROUP) * 256;
-            a.ranges = (p == r->tile_passes - 1) ? r->d_ranges : nullptr;     // the last pass also emits the tile ranges
-            a.ticket = &r->d_counters->ticket[TK_TSORT + p];
-            a.hist = r->d_hist_tile + p * 256;
+            a.n_ptr = num_pairs; a.n_cap = cap;
+            a.status = r->d_status_tile + ((size_t)p * sparts_p + part_off) * 256;
+            a.gstatus = r->d_gstatus_tile + ((size_t)p * gparts_p + part_off / SORT_LB_GROUP) * 256;
+            a.ranges = (p == r->tile_passes - 1) ? r->d_ranges + (half ? r->tiles_cap : 0) : nullptr;   // the last pass also emits the tile ranges
+            a.ticket = &r->d_counters->ticket[(half ? TK_TSORT_FAR : TK_TSORT) + p];
+            a.hist = r->d_hist_tile + half * 4 * 256 + p * 256;
             a.shift = 8u * (uint32_t)p;
             a.err = &r->d_counters->error_flags;
             CU(launch_sort_pass(a, r->grid_sort, stream));
             src ^= 1;
         }
-        r->tile_out = src;
+        *tile_out = src;
+        if (r->timing) CU(cudaEventRecord(r->ev[ev_tsort], stream));
+        return WS_OK;
+    };
+    if (!r->frame_split) return bin_and_tile_sort(0u, 0, EV_BIN, EV_TSORT, &r->tile_out);
+
+    // ---- occlusion split: near slab -> composite into per-pixel state + per-tile saturation -> far slab, whose
+    //      binning drops every splat that only touches saturated tiles (most of them: a tile needs ~1/5 of its list)
+    ws_status st = bin_and_tile_sort(1u, 0, EV_BIN, EV_TSORT, &r->tile_out);
+    if (st != WS_OK) return st;
+    {
+        CompositeArgs a;
+        memset(&a, 0, sizeof a);
+        a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
+        a.uniforms = r->d_uniforms; a.format = (int)r->format;
+        a.mode = 1; a.state = r->d_state; a.tile_done = r->d_tile_done;
+        CU(launch_composite(a, r->h_uniforms.tiles_x, r->h_uniforms.tiles_y, stream));
     }
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_TSORT], stream));
-    return WS_OK;
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_NEAR_BLEND], stream));
+    return bin_and_tile_sort(2u, 1, EV_BIN2, EV_TSORT2, &r->tile_out_far);
 }
 
 // clears + stage 1 + stage 2 of the plain (single-GPU) frame, on `stream`
@@ -972,7 +1014,7 @@ static ws_status enqueue_prepare_body(ws_renderer *r, ws_pointcloud *pc, cudaStr
 {
     const FrameUniforms &U = r->h_uniforms;
     CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
-    CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)U.tiles_x * U.tiles_y * 8, stream));    // {begin, ~end} identities for atomicMin
+    CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)r->tiles_cap * 8 * (r->frame_split ? 2 : 1), stream));    // {begin, ~end} identities for atomicMin
     if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
     {   // ---- stage 1
         PreprocessArgs a;
@@ -994,6 +1036,15 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     if (r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is configured for sharding: use ws_renderer_shard_begin/exchange/finish");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
+    r->frame_split = r->split && r->shard.world == 0;
+    if (r->frame_split) {
+        const size_t px = (size_t)args->viewport[0] * args->viewport[1];
+        if (r->state_px < px) {
+            cudaFree(r->d_state); r->d_state = nullptr; r->state_px = 0;
+            CU(cudaMalloc(&r->d_state, px * sizeof(float4)));
+            r->state_px = px;
+        }
+    }
     st = begin_frame(r, pc, args, pc->n, stream, /*with_clears=*/false);     // uniforms only; capacities may (re)allocate
     if (st != WS_OK) return st;
     if (r->use_graphs && !r->timing) {
@@ -1002,7 +1053,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
         const FrameUniforms &U = r->h_uniforms;
         auto &k = r->prep_key;
         const bool same = r->prep_exec && k.pc == pc && k.gaussians == pc->d_gaussians && k.scratch == r->d_scratch && k.n == pc->n &&
-                          k.W == U.width && k.H == U.height && k.pair_cap == r->pair_cap && k.n_cap == r->n_cap;
+                          k.W == U.width && k.H == U.height && k.pair_cap == r->pair_cap && k.n_cap == r->n_cap &&
+                          k.split == r->frame_split && k.state == (const void *)r->d_state;
         if (!same) {
             if (r->prep_exec) { cudaGraphExecDestroy(r->prep_exec); r->prep_exec = nullptr; }
             if (!r->cap_stream) CU(cudaStreamCreateWithFlags(&r->cap_stream, cudaStreamNonBlocking));
@@ -1016,7 +1068,7 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
             cudaGraphDestroy(g);
             if (e != cudaSuccess) { r->prep_exec = nullptr; return fail_cuda(e, "cudaGraphInstantiate"); }
             k.pc = pc; k.gaussians = pc->d_gaussians; k.scratch = r->d_scratch; k.n = pc->n; k.W = U.width; k.H = U.height;
-            k.pair_cap = r->pair_cap; k.n_cap = r->n_cap;
+            k.pair_cap = r->pair_cap; k.n_cap = r->n_cap; k.split = r->frame_split; k.state = r->d_state;
         }
         CU(cudaGraphLaunch(r->prep_exec, stream));
     } else {
@@ -1178,6 +1230,7 @@ extern "C" ws_status ws_renderer_shard_begin(ws_renderer *r, ws_pointcloud *pc, 
     if (pc->n > s.local_cap) return fail(WS_ERR_INVALID_ARGUMENT, "local shard larger than configured");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
+    r->frame_split = false;
     st = begin_frame(r, pc, args, s.recv_cap, stream);
     if (st != WS_OK) return st;
     if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
@@ -1254,6 +1307,7 @@ extern "C" ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointclo
     if (pc->n > s.local_cap) return fail(WS_ERR_INVALID_ARGUMENT, "local shard larger than configured");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
+    r->frame_split = false;
     st = begin_frame(r, pc, args, s.recv_cap, stream);
     if (st != WS_OK) return st;
     s.epoch += 1;
@@ -1366,7 +1420,12 @@ static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
     CompositeArgs a;
+    memset(&a, 0, sizeof a);
     a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
+    if (r->frame_split) {               // the far slab's list on top of the state the near slab left
+        a.pair_slots = r->d_pslots[r->tile_out_far]; a.ranges = r->d_ranges + r->tiles_cap;
+        a.mode = 2; a.state = r->d_state; a.tile_done = r->d_tile_done;
+    }
     a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
     a.tile_y0 = tile_y0;
     a.signal_flag = r->shard.pending_signal; a.signal_epoch = r->shard.epoch; a.done_counter = &r->d_counters->composite_done;
@@ -1432,7 +1491,8 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
     ws_status st = read_counters(r, &c);
     if (st != WS_OK) return st;
     const FrameUniforms &U = r->h_uniforms;
-    s->num_points = r->last_n; s->num_visible = c.num_visible; s->num_pairs = c.num_pairs;
+    s->num_points = r->last_n; s->num_visible = c.num_visible;
+    s->num_pairs = (uint64_t)c.num_pairs + (r->frame_split ? c.num_pairs_near : 0u);      // split frames: near slab + what the far slab still had to emit
     s->pair_capacity = r->pair_cap; s->num_tiles = U.tiles_x * U.tiles_y; s->width = U.width; s->height = U.height;
     if (r->timing) {
         auto el = [&](int a, int b) { float ms = 0.f; return (cudaEventElapsedTime(&ms, r->ev[a], r->ev[b]) == cudaSuccess) ? ms : 0.f; };
@@ -1441,12 +1501,17 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
         s->ms_binning = el(EV_DSORT, EV_BIN);
         s->ms_tile_sort = el(EV_BIN, EV_TSORT);
         s->ms_ranges = 0.f;                                   // fused into the last tile-sort pass
-        s->ms_sort = el(EV_PRE, EV_TSORT);
         if (r->rendered) s->ms_blend = el(EV_BLEND0, EV_BLEND1);
+        if (r->frame_split) {                                 // near slab | near composite | far slab ... far composite
+            s->ms_binning += el(EV_NEAR_BLEND, EV_BIN2);
+            s->ms_tile_sort += el(EV_BIN2, EV_TSORT2);
+            s->ms_blend += el(EV_TSORT, EV_NEAR_BLEND);
+        }
+        s->ms_sort = s->ms_depth_sort + s->ms_binning + s->ms_tile_sort;
         cudaGetLastError();
     }
     const uint64_t N = r->last_n, V = c.num_visible;
-    const uint64_t P = c.num_pairs < r->pair_cap ? c.num_pairs : r->pair_cap;
+    const uint64_t P = s->num_pairs < r->pair_cap ? s->num_pairs : r->pair_cap;
     const uint64_t T = s->num_tiles;
     const uint64_t rec = r->compressed ? 24 : 28;
     const uint64_t ncoef = (uint64_t)(U.rs.max_sh_deg + 1) * (U.rs.max_sh_deg + 1);
@@ -1454,6 +1519,10 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
     s->bytes_preprocess = N * 12 + N * rec + V * shb + V * (20 + 4 + 4 + 8);   // count (xyz plane) + main
     s->bytes_sort = (uint64_t)r->depth_passes * V * 16 + V * 12 + P * 8 + (uint64_t)r->tile_passes * P * 16 + T * 8;
     s->bytes_blend = P * 24 + T * 8 + (uint64_t)U.width * U.height * bytes_per_pixel(r->format);
+    if (r->frame_split) {                                         // the far slab re-reads the slots + rectangles, the state goes out and in
+        s->bytes_sort += (V / 2) * 12;
+        s->bytes_blend += T * 8 + (uint64_t)U.width * U.height * 32;
+    }
     if (c.error_flags) return fail(WS_ERR_CUDA, "internal: decoupled look-back watchdog fired");
     if (c.pair_overflow) return fail(WS_ERR_PAIR_OVERFLOW, "pair capacity exceeded; raise it with ws_renderer_set_pair_capacity");
     return WS_OK;

@@ -72,7 +72,11 @@ __device__ __forceinline__ void decode_splat(const RawSplat &rs, float fw, float
     D.w = FOOTPRINT_R * (fh * sqrtf(v1y * v1y + v2y * v2y)) + RECT_PAD;
 }
 
-template <int FORMAT>
+// MODE 0: the tile's whole list in one pass.  Occlusion split (two depth slabs, nearest first): MODE 1 walks the near
+// slab's list and leaves {r, g, b, T} per pixel plus a per-tile "every pixel saturated" flag; MODE 2 resumes from that
+// state over the far slab's list (which holds no pair of splats that only touch saturated tiles) and writes the pixels.
+// Per pixel the sequence of blends and early-out tests is exactly that of MODE 0, so the image is bit-identical.
+template <int FORMAT, int MODE>
 __global__ void __launch_bounds__(CB_THREADS)
 composite_kernel(CompositeArgs a)
 {
@@ -106,6 +110,14 @@ composite_kernel(CompositeArgs a)
 
     float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
     bool done = !inside;
+    if (MODE == 2) {
+        if (inside) {
+            const float4 st = a.state[(size_t)py * W + px];
+            cr = st.x; cg = st.y; cb = st.z; T = st.w;
+            done = T < T_EPS;
+        }
+        if (a.tile_done[tile]) range.x = range.y = 0u;   // saturated by the near slab: nothing of the far slab can show
+    }
 
     int32_t remaining = (int32_t)(range.y - range.x);
     uint32_t cursor = range.y;           // walk from the end: nearest first
@@ -183,6 +195,12 @@ composite_kernel(CompositeArgs a)
         buf ^= 1;
     }
 
+    if (MODE == 1) {
+        if (inside) a.state[(size_t)py * W + px] = make_float4(cr, cg, cb, T);
+        const int all_done = __syncthreads_and(done ? 1 : 0);
+        if (tid == 0) a.tile_done[tile] = (uint8_t)(all_done ? 1 : 0);
+        return;
+    }
     if (inside) {
         const float r = cr + a.clear[0] * T, g = cg + a.clear[1] * T, b = cb + a.clear[2] * T;
         const float al = (1.f - T) + a.clear[3] * T;
@@ -215,10 +233,20 @@ composite_kernel(CompositeArgs a)
 cudaError_t launch_composite(const CompositeArgs &a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream)
 {
     dim3 grid(tiles_x, tiles_y);
-    switch (a.format) {
-    case 0: composite_kernel<0><<<grid, CB_THREADS, 0, stream>>>(a); break;
-    case 1: composite_kernel<1><<<grid, CB_THREADS, 0, stream>>>(a); break;
-    default: composite_kernel<2><<<grid, CB_THREADS, 0, stream>>>(a); break;
+    if (a.mode == 1) {
+        composite_kernel<2, 1><<<grid, CB_THREADS, 0, stream>>>(a);          // no pixels are written: the format is irrelevant
+    } else if (a.mode == 2) {
+        switch (a.format) {
+        case 0: composite_kernel<0, 2><<<grid, CB_THREADS, 0, stream>>>(a); break;
+        case 1: composite_kernel<1, 2><<<grid, CB_THREADS, 0, stream>>>(a); break;
+        default: composite_kernel<2, 2><<<grid, CB_THREADS, 0, stream>>>(a); break;
+        }
+    } else {
+        switch (a.format) {
+        case 0: composite_kernel<0, 0><<<grid, CB_THREADS, 0, stream>>>(a); break;
+        case 1: composite_kernel<1, 0><<<grid, CB_THREADS, 0, stream>>>(a); break;
+        default: composite_kernel<2, 0><<<grid, CB_THREADS, 0, stream>>>(a); break;
+        }
     }
     return cudaGetLastError();
 }

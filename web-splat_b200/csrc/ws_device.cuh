@@ -48,7 +48,7 @@ struct FrameCounters {
     uint32_t num_local_visible; // sharded mode: survivors of the local shard (num_visible then counts the received ones)
     uint32_t scatter_done;      // sharded mode: CTAs of the exchange kernel that have finished (last one signals the peers)
     uint32_t composite_done;    // sharded mode: CTAs of the band compositor that have finished
-    uint32_t _r1[1];
+    uint32_t num_pairs_near;    // occlusion split: pairs of the near slab (num_pairs then counts the far slab's)
 };
 
 constexpr int TILE = 16;                    // 16x16 pixel tiles

@@ -64,6 +64,11 @@ struct BinningArgs {
     uint32_t *part_counts;        // ceil(N/1024): pairs per partition (count kernel)
     uint32_t *part_bases;         // ceil(N/1024): exclusive scan (scan kernel)
     uint32_t *hist;               // 4 x 256 tile-id digit histograms (zeroed per frame)
+    // occlusion split: the depth-sorted splats are binned in two slabs, nearest first
+    uint32_t slab;                // 0: all of [0, V);  1: the near slab [split, V);  2: the far slab [0, split),  split = (V/2) & ~3
+    const uint8_t *tile_done;     // slab 2: tiles already saturated by the near slab; a splat whose whole rectangle is done emits no pair
+    uint32_t pair_cap;            // capacity of pair_tiles / pair_slots for this launch
+    uint32_t *num_pairs_out;      // device counter that receives the number of pairs of this launch
 };
 cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand, cudaStream_t stream);
 int binning_blocks_per_sm();
@@ -82,6 +87,11 @@ struct CompositeArgs {
     uint32_t *signal_flag;        // optional (peer-mapped): set to signal_epoch by the last CTA once every pixel store is fenced
     uint32_t signal_epoch;
     uint32_t *done_counter;       // with signal_flag: zeroed per frame
+    // occlusion split: mode 0 = the whole list in one pass; 1 = near slab, per-pixel state {r,g,b,T} + per-tile
+    // "saturated" flag out, no pixels; 2 = far slab, state in, final pixels out
+    int mode;
+    float4 *state;                // W x H
+    uint8_t *tile_done;           // T
 };
 cudaError_t launch_composite(const CompositeArgs &a, uint32_t tiles_x, uint32_t tiles_y, cudaStream_t stream);
 
