@@ -211,14 +211,15 @@ def run_ours(args):
     # same resident cloud; frame i runs in slot i % depth.  At the small configurations one frame's kernels are
     # latency-bound and a second frame fills the idle SMs (cfg1 +36 %, cfg2 +22 %, cfg3 +2 %: profiles/r01o_*).
     depth = int(args.frames_in_flight) if args.frames_in_flight > 0 else 2
-    split = not args.no_occlusion_split
+    split_req = False if args.no_occlusion_split else None        # None = the library's automatic choice (on from 2 M points)
+    split = (not args.no_occlusion_split) and cloud["num_points"] >= 2_000_000
     pair_cap = min(max(8 * cloud["num_points"], 1 << 22), (1 << 30) - 1)
     rs = []
     for _ in range(depth):
         r_ = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
         r_.set_pair_capacity(pair_cap)
         r_.set_timing(False)
-        r_.set_occlusion_split(split)
+        r_.set_occlusion_split(split_req)
         rs.append(r_)
     r = rs[0]                                  # slot 0 also serves the per-stage breakdown below
     fargs = [frame_args(ws, cloud, v, W, H) for v in views]

@@ -253,7 +253,8 @@ WS_API ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled);
  * capacities) instead of 16 launches -- the frame-graph analogue of the reference recording one command
  * buffer per frame (src/lib.rs:415-500).  Default on; this switch exists for A/B measurements. */
 WS_API ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled);
-/* Occlusion split (default on, single-GPU frames): the depth-sorted splats are binned, tile-sorted and composited
+/* Occlusion split (single-GPU frames; enabled: 0 off, 1 on, negative = automatic, the default: on for clouds of at least
+ * 2 M points, where the pairs it saves outweigh its six extra launches): the depth-sorted splats are binned, tile-sorted and composited
  * in two slabs, nearest half first; a splat of the far half whose tiles were all saturated by the near half emits no
  * (tile, splat) pair.  Per pixel the blends and early-out tests are those of the one-pass frame: the image is
  * bit-identical, while num_pairs counts only the pairs that were emitted.  Turn it off to get the complete pair list

@@ -619,8 +619,9 @@ class GaussianRenderer:
         _check(lib().ws_renderer_set_timing(self._h, int(bool(enabled))))
 
     def set_occlusion_split(self, enabled):
-        """Two depth slabs with saturated-tile culling of the far one (default on; bit-identical image, fewer pairs)."""
-        _check(lib().ws_renderer_set_occlusion_split(self._h, int(bool(enabled))))
+        """Two depth slabs with saturated-tile culling of the far one (bit-identical image, fewer pairs).
+        True / False, or None for the default: automatic (on from 2 M points)."""
+        _check(lib().ws_renderer_set_occlusion_split(self._h, -1 if enabled is None else int(bool(enabled))))
 
     def set_cuda_graphs(self, enabled):
         _check(lib().ws_renderer_set_cuda_graphs(self._h, int(bool(enabled))))

@@ -708,7 +708,7 @@ struct ws_renderer {
     // CUDA graph of one prepare() (clears + 14 kernels), replayed while (cloud, viewport, capacities) stay the same
     bool use_graphs = true;
     // occlusion split (two depth slabs, nearest first)
-    bool split = true;                     // requested (ws_renderer_set_occlusion_split)
+    int split_mode = 2;                    // 0 off, 1 on, 2 auto (ws_renderer_set_occlusion_split)
     bool frame_split = false;              // the prepared frame was built split
     float4 *d_state = nullptr; size_t state_px = 0;   // per pixel {r, g, b, T} after the near slab
     uint8_t *d_tile_done = nullptr;        // per tile: saturated by the near slab
@@ -796,12 +796,12 @@ extern "C" ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled
     return WS_OK;
 }
 
-// Occlusion split on/off (default on; the sharded paths never split).  Off = one binning + tile sort over all P pairs,
+// Occlusion split: 0 off, 1 on, negative = automatic (the default: on from 2 M points; the sharded paths never split).  Off = one binning + tile sort over all P pairs,
 // which is what the pair-list read-backs (WS_BUF_PAIR_*, WS_BUF_TILE_RANGES) and num_pairs describe exactly.
 extern "C" ws_status ws_renderer_set_occlusion_split(ws_renderer *r, int32_t enabled)
 {
     if (!r) return fail(WS_ERR_INVALID_ARGUMENT, "NULL renderer");
-    r->split = enabled != 0;
+    r->split_mode = enabled < 0 ? 2 : (enabled ? 1 : 0);
     return WS_OK;
 }
 
@@ -833,10 +833,10 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         const size_t o_pb = off; off = align_up(off + parts256 * 4, 256);
         const size_t o_bb = off; off = align_up(off + parts256 * 4, 256);
         const size_t o_sd = off; off = align_up(off + 4 * sparts_n * 256 * 4, 256);
-        const size_t o_st = off; off = align_up(off + 3 * sparts_p * 256 * 4, 256);
+        const size_t o_st = off; off = align_up(off + 2 * 3 * sparts_p * 256 * 4, 256);     // x2: one set per depth slab
         const size_t gparts_n = (sparts_n + SORT_LB_GROUP - 1) / SORT_LB_GROUP, gparts_p = (sparts_p + SORT_LB_GROUP - 1) / SORT_LB_GROUP;
         const size_t o_gd = off; off = align_up(off + 4 * gparts_n * 256 * 4, 256);
-        const size_t o_gt = off; off = align_up(off + 3 * gparts_p * 256 * 4, 256);
+        const size_t o_gt = off; off = align_up(off + 2 * 3 * gparts_p * 256 * 4, 256);
         CU(cudaMalloc(&r->d_scratch, off));
         r->scratch_bytes = off;
         r->d_counters = reinterpret_cast<FrameCounters *>(r->d_scratch + o_counters);
@@ -953,14 +953,14 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_DSORT], stream));
     // ---- stage 2b + 2c for one slab of the depth-sorted splats: expand into (tile, slot) pairs in depth order, then the
-    //      tile-id passes on those pairs.  `half` selects the slab's private half of the look-back status words, digit
+    //      tile-id passes on those pairs.  `half` selects the slab's private set of look-back status words, digit
     //      histograms, tickets and tile ranges (the pair buffers themselves are reused: the slabs run back to back).
     auto bin_and_tile_sort = [&](uint32_t slab, int half, int ev_bin, int ev_tsort, int *tile_out) -> ws_status {
         const size_t sparts_p = ((size_t)r->pair_cap + SORT_PART - 1) / SORT_PART;
         const size_t gparts_p = (sparts_p + SORT_LB_GROUP - 1) / SORT_LB_GROUP;
-        // split frames give each slab half of the status words, hence half of the pair capacity (whole look-back groups)
-        const size_t part_off = half ? (sparts_p / 2 / SORT_LB_GROUP) * SORT_LB_GROUP : 0;
-        const uint32_t cap = (slab == 0u) ? r->pair_cap : (uint32_t)(((sparts_p / 2 / SORT_LB_GROUP) * SORT_LB_GROUP) * SORT_PART);
+        // each slab has its own set of look-back status words (the second set starts after the 3 passes of the first)
+        const size_t set_off = half ? 3 * sparts_p : 0, gset_off = half ? 3 * gparts_p : 0;
+        const uint32_t cap = r->pair_cap;
         uint32_t *num_pairs = (slab == 1u) ? &r->d_counters->num_pairs_near : &r->d_counters->num_pairs;
         {
             BinningArgs a;
@@ -977,8 +977,8 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
             a.keys_in = r->d_ptiles[src]; a.vals_in = r->d_pslots[src];
             a.keys_out = r->d_ptiles[src ^ 1]; a.vals_out = r->d_pslots[src ^ 1];
             a.n_ptr = num_pairs; a.n_cap = cap;
-            a.status = r->d_status_tile + ((size_t)p * sparts_p + part_off) * 256;
-            a.gstatus = r->d_gstatus_tile + ((size_t)p * gparts_p + part_off / SORT_LB_GROUP) * 256;
+            a.status = r->d_status_tile + (set_off + (size_t)p * sparts_p) * 256;
+            a.gstatus = r->d_gstatus_tile + (gset_off + (size_t)p * gparts_p) * 256;
             a.ranges = (p == r->tile_passes - 1) ? r->d_ranges + (half ? r->tiles_cap : 0) : nullptr;   // the last pass also emits the tile ranges
             a.ticket = &r->d_counters->ticket[(half ? TK_TSORT_FAR : TK_TSORT) + p];
             a.hist = r->d_hist_tile + half * 4 * 256 + p * 256;
@@ -1036,7 +1036,9 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     if (r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is configured for sharding: use ws_renderer_shard_begin/exchange/finish");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
-    r->frame_split = r->split && r->shard.world == 0;
+    // auto: the six extra launches and the state round trip pay off only when there are many pairs to save -- measured
+    // cfg 1 (100 K points) -14 %, cfg 2 (1 M) -2 %, cfg 3 (6 M) +7 %
+    r->frame_split = r->shard.world == 0 && (r->split_mode == 1 || (r->split_mode == 2 && pc->n >= 2000000u));
     if (r->frame_split) {
         const size_t px = (size_t)args->viewport[0] * args->viewport[1];
         if (r->state_px < px) {
