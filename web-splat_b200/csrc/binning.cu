@@ -40,7 +40,7 @@ constexpr int BIN_ROUNDS = 8;                         // output positions per th
 constexpr int BIN_CAP = BIN_THREADS * BIN_ROUNDS;     // 2048 pairs per chunk
 constexpr int BIN_NDIG = 3;
 
-struct SplatRects { uint32_t slot[BIN_SPT], xy[BIN_SPT], w[BIN_SPT], cnt[BIN_SPT]; };
+struct SplatRects { uint32_t slot[BIN_SPT], xy[BIN_SPT], w[BIN_SPT], h[BIN_SPT], cnt[BIN_SPT]; };
 
 // the range of depth-sorted positions this launch expands (ascending key = far -> near, so the near slab is the upper one);
 // the split point is a multiple of 4 so that the 16-byte slot loads stay aligned
@@ -51,8 +51,9 @@ __device__ __forceinline__ void slab_bounds(const BinningArgs &a, uint32_t V, ui
     hi = (a.slab == 2u) ? split : V;
 }
 
-// slots + rectangles of the BIN_SPT consecutive depth-sorted splats of one thread (positions first .. first+3, below V)
-__device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first, uint32_t V, SplatRects &r)
+// slots + rectangles of the BIN_SPT consecutive depth-sorted splats of one thread (positions first .. first+3, below V).
+// keep4: one byte per splat, 0 = emits no pair (far slab, decided by the count kernel); 0x01010101 when there is no filter.
+__device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first, uint32_t V, SplatRects &r, uint32_t keep4 = 0x01010101u)
 {
     if (first + BIN_SPT <= V) {
         const uint4 s4 = *reinterpret_cast<const uint4 *>(a.sorted_slots + first);
@@ -63,29 +64,36 @@ __device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first,
     }
     uint2 rc[BIN_SPT];
 #pragma unroll
-    for (int j = 0; j < BIN_SPT; j++) rc[j] = (r.slot[j] != 0xffffffffu) ? __ldg(a.rects + r.slot[j]) : make_uint2(0u, 0u);
+    for (int j = 0; j < BIN_SPT; j++)
+        rc[j] = (r.slot[j] != 0xffffffffu && ((keep4 >> (8 * j)) & 0xffu)) ? __ldg(a.rects + r.slot[j]) : make_uint2(0u, 0u);
 #pragma unroll
     for (int j = 0; j < BIN_SPT; j++) {
         r.xy[j] = rc[j].x;
         r.w[j] = rc[j].y & 0xffffu;
-        r.cnt[j] = r.w[j] * (rc[j].y >> 16);
+        r.h[j] = rc[j].y >> 16;
+        r.cnt[j] = r.w[j] * r.h[j];
     }
-    if (a.tile_done) {
-        // far slab: a splat all of whose tiles were saturated by the near slab cannot change a pixel.  Only small
-        // rectangles are tested (they are almost all of them); a pair emitted for a saturated tile is harmless,
-        // the compositor skips that tile.
-        const uint32_t tiles_x = a.uniforms->tiles_x;
+}
+
+// far slab: a splat all of whose tiles were saturated by the near slab cannot change a pixel.  Only small rectangles are
+// tested (they are almost all of them); a pair emitted for a saturated tile is harmless, the compositor skips that tile.
+// Returns the keep bytes for load_rects (the expand kernel does not repeat the test, nor fetch the dropped rectangles).
+__device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRects &r)
+{
+    const uint32_t tiles_x = a.uniforms->tiles_x;
+    uint32_t keep4 = 0u;
 #pragma unroll
-        for (int j = 0; j < BIN_SPT; j++) {
-            if (r.cnt[j] > 0u && r.cnt[j] <= 16u) {
-                const uint32_t x0 = r.xy[j] & 0xffffu, y0 = r.xy[j] >> 16, h = rc[j].y >> 16;
-                bool all = true;
-                for (uint32_t yy = 0; yy < h; yy++)
-                    for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (a.tile_done[(y0 + yy) * tiles_x + x0 + xx] != 0);
-                if (all) r.cnt[j] = 0u;
-            }
+    for (int j = 0; j < BIN_SPT; j++) {
+        if (r.cnt[j] > 0u && r.cnt[j] <= 16u) {
+            const uint32_t x0 = r.xy[j] & 0xffffu, y0 = r.xy[j] >> 16;
+            bool all = true;
+            for (uint32_t yy = 0; yy < r.h[j]; yy++)
+                for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (a.tile_done[(y0 + yy) * tiles_x + x0 + xx] != 0);
+            if (all) r.cnt[j] = 0u;
         }
+        if (r.cnt[j] > 0u) keep4 |= 1u << (8 * j);
     }
+    return keep4;
 }
 
 // ---- (1) COUNT ---------------------------------------------------------------------------------
@@ -101,6 +109,7 @@ bin_count_kernel(BinningArgs a)
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         SplatRects r;
         load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r);
+        if (a.tile_done) a.keep4[part * BIN_THREADS + tid] = drop_saturated(a, r);
         uint32_t c = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -158,7 +167,7 @@ bin_expand_kernel(BinningArgs a)
 
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         SplatRects r;
-        load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r);
+        load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r, a.tile_done ? a.keep4[part * BIN_THREADS + tid] : 0x01010101u);
         const uint32_t base = __ldg(a.part_bases + part);
         const uint32_t mine = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
         // block scan of the per-thread totals

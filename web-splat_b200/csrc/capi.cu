@@ -712,6 +712,7 @@ struct ws_renderer {
     bool frame_split = false;              // the prepared frame was built split
     float4 *d_state = nullptr; size_t state_px = 0;   // per pixel {r, g, b, T} after the near slab
     uint8_t *d_tile_done = nullptr;        // per tile: saturated by the near slab
+    uint32_t *d_keep4 = nullptr;           // far slab: one byte per splat, written by bin_count, read by bin_expand
     int tile_out_far = 0;
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t prep_exec = nullptr;
@@ -730,6 +731,7 @@ static void free_sort_stuff(ws_renderer *r)
         cudaFree(r->d_pslots[i]); r->d_pslots[i] = nullptr;
     }
     cudaFree(r->d_rects); r->d_rects = nullptr;
+    cudaFree(r->d_keep4); r->d_keep4 = nullptr;
     r->n_cap = 0; r->pair_cap = 0;
 }
 
@@ -858,6 +860,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
             CU(cudaMalloc(&r->d_pslots[i], (size_t)pair_cap * 4));
         }
         CU(cudaMalloc(&r->d_rects, nn * 8));
+        CU(cudaMalloc(&r->d_keep4, (nn / 2 + 2 * 1024 + 4) / 4 * 4 + 4096));   // far slab rounded up to whole 1024-splat partitions
         r->n_cap = n; r->pair_cap = pair_cap;
     }
     if (!r->d_ranges || r->tiles_cap < tiles) {
@@ -968,6 +971,7 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
             a.counters = r->d_counters; a.pair_tiles = r->d_ptiles[0]; a.pair_slots = r->d_pslots[0];
             a.part_counts = r->d_scan_bin; a.part_bases = r->d_bin_bases; a.hist = r->d_hist_tile + half * 4 * 256;
             a.slab = slab; a.tile_done = (slab == 2u) ? r->d_tile_done : nullptr; a.pair_cap = cap; a.num_pairs_out = num_pairs;
+            a.keep4 = r->d_keep4;
             CU(launch_binning(a, r->ctx->sm_count * 8, r->grid_bin, stream));
         }
         if (r->timing) CU(cudaEventRecord(r->ev[ev_bin], stream));
