@@ -331,7 +331,8 @@ def run_ours(args):
     # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture (cfg3 only)
     traffic = None
     try:
-        if args.workload == "cfg3":
+        # the capture is of the one-pass frame; the split frame's binning / tile-sort / composite launches move other amounts
+        if args.workload == "cfg3" and (not split or dom in ("preprocess", "depth_sort_pass")):
             tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic_cfg3.json")))
             key = {"composite": "composite_kernel<1>", "preprocess": "preprocess_kernel<0>", "binning": "bin_expand_kernel",
                    "tile_sort_pass": "onesweep_pass_kernel<1>", "depth_sort_pass": "onesweep_pass_kernel<0>"}[dom]
@@ -342,7 +343,7 @@ def run_ours(args):
     evals = P * 256.0                                  # pixel-splat evaluations if every staged splat met every pixel
     roofline = {
         "kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": "profiles/kernel_traffic_cfg3.json (ncu --set full, r01m)",
+        "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": "profiles/kernel_traffic_cfg3.json (ncu --set full, r01m: one-pass frame; null for the kernels the occlusion split changes)",
         "peak_source": peak_src,
         "note": "stage 3 is FP32/MUFU-issue bound, not HBM bound (SURVEY 8(d)); its HBM fraction is reported because "
                 "the north star asks for it; 'blend_alu' gives pixel-splat evaluations/s against the MUFU ex2 bound",
