@@ -328,22 +328,26 @@ def run_ours(args):
     for kv in kernels.values():
         kv["gbs"] = gbs(kv["bytes"], kv["ms"]); kv["frac"] = kv["gbs"] / peak
     dom = max(kernels, key=lambda k_: kernels[k_]["ms"] * kernels[k_].get("launches", 1))
-    # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture (cfg3 only)
-    traffic = None
+    # DRAM traffic of the dominant kernel (same unit of work as its `bytes`) from the committed ncu --set full captures (cfg3 only)
+    traffic, traffic_src = None, None
     try:
-        # the capture is of the one-pass frame; the split frame's binning / tile-sort / composite launches move other amounts
-        if args.workload == "cfg3" and (not split or dom in ("preprocess", "depth_sort_pass")):
+        if args.workload == "cfg3" and split:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic_cfg3_split.json")))
+            traffic = tj["per_stage"][dom]["dram_bytes"]
+            traffic_src = "profiles/kernel_traffic_cfg3_split.json (ncu --set full, r01q, occlusion split: %s)" % tj["per_stage"][dom]["launches"]
+        elif args.workload == "cfg3":
             tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic_cfg3.json")))
             key = {"composite": "composite_kernel<1>", "preprocess": "preprocess_kernel<0>", "binning": "bin_expand_kernel",
                    "tile_sort_pass": "onesweep_pass_kernel<1>", "depth_sort_pass": "onesweep_pass_kernel<0>"}[dom]
             traffic = tj[key]["dram_bytes_per_launch"]
+            traffic_src = "profiles/kernel_traffic_cfg3.json (ncu --set full, r01m, one-pass frame)"
     except Exception:
         traffic = None
     clk = (clocks["sm_mhz"] or sm_max) * 1e6
     evals = P * 256.0                                  # pixel-splat evaluations if every staged splat met every pixel
     roofline = {
         "kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": "profiles/kernel_traffic_cfg3.json (ncu --set full, r01m: one-pass frame; null for the kernels the occlusion split changes)",
+        "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src,
         "note": "stage 3 is FP32/MUFU-issue bound, not HBM bound (SURVEY 8(d)); its HBM fraction is reported because "
                 "the north star asks for it; 'blend_alu' gives pixel-splat evaluations/s against the MUFU ex2 bound",
