@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "frames/sec"
+REFERENCE_BUDGET_S = 120.0                  # host seconds the reference arm may spend on timed frames
 KERNELS_STAGE1 = 3                          # count, scan, preprocess
 KERNELS_BINNING = 3                         # count, scan, expand (per slab; the tile ranges are fused into the last onesweep pass)
 
@@ -155,8 +156,21 @@ def run_reference(args):
     cloud, W, H, views = make_workload(args.workload)
     from oracle import oracle as orc
     orc.build()
-    for i in range(args.warmup):
+    # The driver launches this arm with the GPU arm's --steps / --warmup (hundreds of steps); a CPU frame of cfg3 takes
+    # seconds.  The sample is therefore bounded: at most 3 warm-up frames, then as many FULL frames of the orbit as fit
+    # REFERENCE_BUDGET_S (never fewer than 1, never more than --steps); `steps` reports the frames actually timed.
+    t_frame = None
+    for i in range(min(args.warmup, 3)):
+        t1 = time.perf_counter()
         oracle_frame_seconds(cloud, views[i % len(views)], W, H)
+        t_frame = time.perf_counter() - t1
+    if t_frame is None:
+        t1 = time.perf_counter()
+        oracle_frame_seconds(cloud, views[0], W, H)
+        t_frame = time.perf_counter() - t1
+    timed = max(1, min(args.steps, int(REFERENCE_BUDGET_S / max(t_frame, 1e-6))))
+    requested = args.steps
+    args.steps = timed
     t0 = time.perf_counter()
     for i in range(args.steps):
         oracle_frame_seconds(cloud, views[i % len(views)], W, H)
@@ -165,12 +179,14 @@ def run_reference(args):
     cores = orc.num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cloud, W, H), "views": len(views)},
+        "config": {"workload": workload_name(args.workload, cloud, W, H), "views": len(views),
+                   "steps_requested": requested, "warmup_requested": args.warmup},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d full frames of the same workload on the CPU oracle (OpenMP, %d threads); the reference "
-                                   "itself (Rust+WGSL on wgpu/Vulkan) cannot be built or run on this box" % (args.steps, cores)},
+                         "sample": "%d full frames of the same workload on the CPU oracle (OpenMP, %d threads; %d steps were requested, "
+                                   "the sample is bounded to ~%d s of host time); the reference itself (Rust+WGSL on wgpu/Vulkan) "
+                                   "cannot be built or run on this box" % (args.steps, cores, requested, int(REFERENCE_BUDGET_S))},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -20,7 +20,7 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "frames/sec" and d["unit"] == "frames/s" and d["higher_is_better"] is True
-    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1.0
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["config"]["steps_requested"] == 2 and d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1.0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("cfg1: 100000 synthetic Gaussians")
