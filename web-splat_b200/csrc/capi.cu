@@ -1554,9 +1554,10 @@ extern "C" ws_status ws_renderer_read_buffer(ws_renderer *r, ws_buffer_id which,
     case WS_BUF_SORTED_INDICES: src = r->d_vals[r->depth_out]; bytes = V * 4; break;
     case WS_BUF_SORTED_KEYS: src = r->d_keys[r->depth_out]; bytes = V * 4; break;
     case WS_BUF_TILE_RECTS: src = r->d_rects; bytes = V * 8; break;
-    case WS_BUF_PAIR_TILES: src = r->d_ptiles[r->tile_out]; bytes = P * 4; break;
-    case WS_BUF_PAIR_SLOTS: src = r->d_pslots[r->tile_out]; bytes = P * 4; break;
-    case WS_BUF_TILE_RANGES: src = r->d_ranges; bytes = T * 8; break;
+    // split frames: the pair buffers hold the far slab's list when the frame is over (c.num_pairs = its size)
+    case WS_BUF_PAIR_TILES: src = r->d_ptiles[r->frame_split ? r->tile_out_far : r->tile_out]; bytes = P * 4; break;
+    case WS_BUF_PAIR_SLOTS: src = r->d_pslots[r->frame_split ? r->tile_out_far : r->tile_out]; bytes = P * 4; break;
+    case WS_BUF_TILE_RANGES: src = r->d_ranges + (r->frame_split ? r->tiles_cap : 0); bytes = T * 8; break;
     default: return fail(WS_ERR_INVALID_ARGUMENT, "unknown buffer id");
     }
     if (written) *written = bytes;
