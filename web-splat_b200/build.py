@@ -77,7 +77,32 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(p.stdout + p.stderr)
             raise RuntimeError("link failed")
+    build_tools(force=force)
     return OUT, logs
+
+
+TOOLS_DIR = os.path.normpath(os.path.join(HERE, "..", "tools"))
+TOOL_OUT = os.path.join(HERE, "ws_render")
+
+
+def build_tools(force=False):
+    """tools/ws_render.cpp: the offline dataset renderer in C++ on top of the C ABI (header-only mirror include/websplat_b200.hpp)."""
+    src = os.path.join(TOOLS_DIR, "ws_render.cpp")
+    inc = os.path.normpath(os.path.join(HERE, "..", "include"))
+    deps = [src, os.path.join(inc, "websplat_b200.hpp"), os.path.join(inc, "websplat_b200.h"), OUT]
+    if not os.path.exists(src):
+        return None
+    if force or _stale(TOOL_OUT, deps):
+        cxx = os.environ.get("CXX") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++")
+        cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", TOOL_OUT, src, "-L" + HERE, "-lwebsplat_b200",
+               "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread", "-lrt"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError("building tools/ws_render.cpp failed")
+        if p.stderr.strip():
+            sys.stderr.write(p.stderr)
+    return TOOL_OUT
 
 
 if __name__ == "__main__":
