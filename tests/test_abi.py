@@ -69,7 +69,7 @@ def test_no_cpu_fallback_without_gpu(ws):
 def test_product_does_not_import_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
     pats = (r'#\s*include\s*[<"][^>"]*oracle', r"libws_oracle", r"^\s*from\s+oracle\b", r"^\s*import\s+oracle\b", r"wso_[a-z_]+\s*\(")
-    roots = [os.path.join(ROOT, d) for d in ("web-splat_b200", "include", "scripts", "bindings")]
+    roots = [os.path.join(ROOT, d) for d in ("web-splat_b200", "include", "scripts", "bindings", "tools")]
     files = [os.path.join(ROOT, f) for f in ("bench_multi.py", "websplat_b200.py")]
     for root in roots:
         for dirpath, _, names in os.walk(root):
