@@ -79,3 +79,19 @@ def test_product_does_not_import_oracle():
             txt = open(path, errors="ignore").read()
             for pat in pats:
                 assert not re.search(pat, txt, re.M), (path, pat)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """the drop-in boundary must be consumable from C (cgo / JNI / Rust bindgen read it as C) and from C++."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "websplat_b200.h"\nint main(void) { ws_splatting_args a; ws_frame_stats s; (void)a; (void)s; return sizeof(ws_pointcloud_desc) > 0 ? 0 : 1; }\n')
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    p = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(c)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "websplat_b200.hpp"\nint main() { ws::SplattingArgs a; return a.c().max_sh_deg == 3 ? 0 : 1; }\n')
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    p = subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(cpp)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
