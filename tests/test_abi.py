@@ -95,3 +95,42 @@ def test_header_is_plain_c_and_cxx(tmp_path):
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     p = subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(cpp)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+
+
+def test_ctypes_mirror_has_the_header_s_struct_layouts(ws, tmp_path):
+    """sizeof / offsetof of every struct that crosses the boundary: the C header against the ctypes mirror."""
+    import ctypes as C
+    import subprocess
+    structs = {"ws_aabb": ws.ws_aabb, "ws_quantization4": ws.ws_quantization4, "ws_pointcloud_desc": ws.ws_pointcloud_desc,
+               "ws_splatting_args": ws.ws_splatting_args, "ws_frame_stats": ws.ws_frame_stats, "ws_c3dgs_arrays": ws.ws_c3dgs_arrays,
+               "ws_ply_info": ws.ws_ply_info}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "websplat_b200.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in st._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"; src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    p = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for name, st in structs.items():
+        assert int(got[name]) == C.sizeof(st), name
+        for field, _ in st._fields_:
+            assert int(got["%s.%s" % (name, field)]) == getattr(st, field).offset, (name, field)
+
+
+def test_rust_ffi_structs_list_the_header_s_fields_in_order(ws):
+    """bindings/rust cannot be compiled here; at least its #[repr(C)] structs must name the same fields in the same order."""
+    txt = open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    for name, st in (("ws_aabb", ws.ws_aabb), ("ws_quantization4", ws.ws_quantization4), ("ws_pointcloud_desc", ws.ws_pointcloud_desc),
+                     ("ws_splatting_args", ws.ws_splatting_args), ("ws_frame_stats", ws.ws_frame_stats)):
+        m = re.search(r"pub struct %s\s*\{(.*?)\}" % name, txt, re.S)
+        assert m, name
+        rust_fields = re.findall(r"pub (\w+)\s*:", m.group(1))
+        assert rust_fields == [f for f, _ in st._fields_], name
+    # every function the crate declares exists in the library
+    declared = re.findall(r"pub fn (ws_\w+)\(", txt)
+    assert declared and set(declared) <= set(ws.EXPORTED_SYMBOLS)
