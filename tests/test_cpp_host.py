@@ -76,7 +76,7 @@ def test_cpp_tool_errors(ws, tool, tmp_path):
     assert subprocess.run([tool], capture_output=True).returncode == 64
     ply = tmp_path / "c.ply"; ply.write_bytes(ws.synth.ply_bytes(ws.synth.ply_vertices(50, 1, 1), 1))
     cams = tmp_path / "cameras.json"; cams.write_text(json.dumps(_scene_entries(ws, 3, 320, 200)))
-    notply = tmp_path / "c.bin"; notply.write_bytes(b"PK\x03\x04....")
+    notply = tmp_path / "c.bin"; notply.write_bytes(b"not a splat file")
     p = subprocess.run([tool, str(notply), str(cams), str(tmp_path / "o")], capture_output=True, text=True)
     assert p.returncode == 1 and "Unknown file format" in p.stderr
     try:
@@ -106,3 +106,57 @@ def test_gpu_cpp_tool_renders_like_the_python_tool(ws, ctx, tool, tmp_path):
         assert names == sorted(os.listdir(b / split)) and names
         for nm in names:
             assert np.array_equal(ws.scene.decode_png((a / split / nm).read_bytes()), ws.scene.decode_png((b / split / nm).read_bytes()))
+
+
+def _fnv1a(b):
+    h = 1469598103934665603
+    for x in bytes(b):
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("compressed_zip", [False, True])
+def test_cpp_npz_reader_matches_numpy(ws, tool, tmp_path, compressed_zip):
+    """tools/npz_reader.hpp (zip central directory, zip64 extras as numpy writes them, stored / deflated members, .npy headers)."""
+    a = ws.synth.c3dgs_arrays(700, 4, 2, codebook=64)
+    a["extra_f8"] = np.float64(2.5); a["extra_i8"] = np.arange(6, dtype=np.int64).reshape(2, 3)
+    path = tmp_path / "c.npz"
+    (np.savez_compressed if compressed_zip else np.savez)(path, **a)
+    p = subprocess.run([tool, "--parse-npz", str(path)], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    got = {}
+    for line in p.stdout.strip().splitlines():
+        left, right = line.split(" | ")
+        f = left.split()
+        got[f[0]] = (f[1], tuple(int(x) for x in f[2:]), int(right.split()[0]), int(right.split()[1], 16))
+    assert set(got) == set(a)
+    for k, v in a.items():
+        v = np.asarray(v)
+        descr, shape, nbytes, h = got[k]
+        assert descr == v.dtype.str and shape == v.shape and nbytes == v.nbytes and h == _fnv1a(np.ascontiguousarray(v).tobytes()), k
+    # the descriptor the loader hands to ws_pointcloud_create_from_c3dgs (io/npz.rs:29-160)
+    q = subprocess.run([tool, "--check-npz", str(path)], capture_output=True, text=True, timeout=60)
+    assert q.returncode == 0, q.stderr
+    lines = q.stdout.strip().splitlines()
+    assert lines[0] == "points 700 covars 64 features 64 sh_deg 2 scaling_factor 1 gaussian_indices 1 feature_indices 1"
+    f = lines[1].split()
+    assert abs(float(f[1]) - float(a["scaling_scale"])) < 1e-9 and int(f[2]) == a["scaling_zero_point"]
+    assert abs(float(f[4]) - float(a["rotation_scale"])) < 1e-9 and int(f[5]) == a["rotation_zero_point"]
+    for line, key in zip(lines[2:6], ("features_dc", "features_rest", "opacity", "scaling_factor")):
+        zp, sc = line.split()[1:]
+        assert int(zp) == a[key + "_zero_point"] and abs(float(sc) - float(a[key + "_scale"])) < 1e-9
+    assert lines[6].startswith("meta mip 1 1 kernel 1 0.1") and lines[6].endswith("bg 1 0 0 0")
+    assert lines[7] == "gi0 %d gilast %d" % (a["gaussian_indices"][0], a["gaussian_indices"][-1])
+    # the older file variant: no scaling factor, no index arrays, no metadata
+    b = ws.synth.c3dgs_arrays(50, 5, 0, scaling_factor=False, indices=False, metadata=False)
+    path2 = tmp_path / "d.npz"; np.savez(path2, **b)
+    q = subprocess.run([tool, "--check-npz", str(path2)], capture_output=True, text=True, timeout=60)
+    assert q.returncode == 0 and q.stdout.splitlines()[0] == "points 50 covars 50 features 50 sh_deg 0 scaling_factor 0 gaussian_indices 0 feature_indices 0"
+    assert "quant 0 1" in q.stdout.splitlines()[5] and q.stdout.splitlines()[6].startswith("meta mip 0 0 kernel 0 0 bg 0")
+    # a missing required member is an error (io/npz.rs:265-275), so is a truncated archive
+    del b["rotation"]
+    path3 = tmp_path / "e.npz"; np.savez(path3, **b)
+    r = subprocess.run([tool, "--check-npz", str(path3)], capture_output=True, text=True)
+    assert r.returncode == 1 and "rotation" in r.stderr
+    path4 = tmp_path / "f.npz"; path4.write_bytes(path.read_bytes()[:-30])
+    assert subprocess.run([tool, "--parse-npz", str(path4)], capture_output=True, text=True).returncode == 1

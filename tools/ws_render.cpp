@@ -1,13 +1,17 @@
 // ws_render -- offline dataset renderer on top of the C ABI, in C++ (the compiled-language counterpart of the reference's
 // `render` binary, bin/render.rs:14-180; scripts/render_scene.py is the same tool in Python).
 //
-//   ws_render <input.ply> <cameras.json> <img_out> [--max-sh-deg N]     renders the test split, then the train split, to PNG
+//   ws_render <input.ply|.npz> <cameras.json> <img_out> [--max-sh-deg N]   renders the test split, then the train split, to PNG
 //   ws_render --parse-scene <cameras.json>                              prints what Scene::from_json + Into<PerspectiveCamera> give (no GPU)
 //   ws_render --png-selftest <out.png> <width> <height>                 writes a synthetic f16 frame through the pixel conversion + PNG writer (no GPU)
 //
-// Only .ply input here: the .npz container (zip + npy) is decoded by the caller's language runtime in both mirrors; the ABI
-// entry for its arrays is ws_pointcloud_create_from_c3dgs.  PNG files use stored (uncompressed) deflate blocks: no zlib needed.
+//   ws_render --parse-npz <file.npz>                                    lists the members of a .npz (name, dtype, shape, FNV-1a of the bytes; no GPU)
+//
+// Input: .ply, or the compressed .npz of io/npz.rs (tools/npz_reader.hpp decodes the zip + npy container -- deflated members
+// need the zlib build --, the arrays go to the GPU through ws_pointcloud_create_from_c3dgs).  PNG files use stored
+// (uncompressed) deflate blocks, so writing them needs no zlib.
 #include "../include/websplat_b200.hpp"
+#include "npz_reader.hpp"
 
 #include <cctype>
 #include <cstdio>
@@ -121,6 +125,90 @@ ws::Scene scene_from_json(const std::string &text)
     return ws::Scene::from_file_order(std::move(cams));
 }
 
+// ---- compressed .npz -> ws_c3dgs_arrays: NpzReader::new + read (io/npz.rs:29-56,58-160), minus the GPU part ---------------
+const npz::Array &need(const std::map<std::string, npz::Array> &m, const char *name, const char *descr)
+{
+    auto it = m.find(name);
+    if (it == m.end()) throw std::runtime_error(std::string("array '") + name + "' missing");                  // io/npz.rs:265-275
+    if (it->second.descr != descr) throw std::runtime_error(std::string("array '") + name + "' has dtype " + it->second.descr + ", expected " + descr);
+    return it->second;
+}
+const npz::Array *maybe(const std::map<std::string, npz::Array> &m, const char *name)
+{
+    auto it = m.find(name);
+    return it == m.end() ? nullptr : &it->second;
+}
+double scalar_or(const std::map<std::string, npz::Array> &m, const std::string &name, double dflt)
+{
+    auto it = m.find(name);
+    return (it == m.end() || it->second.count() == 0) ? dflt : it->second.as_double(0);
+}
+
+// the descriptor points into `m` (and into gi / fi when an index array had to be widened): keep them alive
+ws_c3dgs_arrays c3dgs_from_members(const std::map<std::string, npz::Array> &m, std::vector<int32_t> &gi, std::vector<int32_t> &fi)
+{
+    ws_c3dgs_arrays d;
+    std::memset(&d, 0, sizeof d);
+    const npz::Array &xyz = need(m, "xyz", "<f2"), &opacity = need(m, "opacity", "|i1");
+    const npz::Array &scaling = need(m, "scaling", "|i1"), &rotation = need(m, "rotation", "|i1");
+    const npz::Array &dc = need(m, "features_dc", "|i1"), &rest = need(m, "features_rest", "|i1");
+    const size_t n = xyz.count() / 3;
+    if (opacity.count() != n) throw std::runtime_error("opacity has a different length than xyz");
+    d.xyz = xyz.data.data(); d.opacity = reinterpret_cast<const int8_t *>(opacity.data.data()); d.num_points = n;
+    const bool has_sf = maybe(m, "scaling_factor_scale") != nullptr;                                           // io/npz.rs:88-96
+    if (has_sf) {
+        const npz::Array &sf = need(m, "scaling_factor", "|i1");
+        if (sf.count() != n) throw std::runtime_error("scaling_factor has a different length than xyz");
+        d.scaling_factor = reinterpret_cast<const int8_t *>(sf.data.data());
+    }
+    auto indices = [&](const char *name, std::vector<int32_t> &store) -> const int32_t * {
+        const npz::Array *a = maybe(m, name);
+        if (!a) return nullptr;
+        if (a->count() != n) throw std::runtime_error(std::string(name) + " has a different length than xyz");
+        if (a->descr == "<i4") return reinterpret_cast<const int32_t *>(a->data.data());
+        store.resize(n);
+        for (size_t i = 0; i < n; i++) store[i] = (int32_t)a->as_double(i);
+        return store.data();
+    };
+    d.gaussian_indices = indices("gaussian_indices", gi);
+    d.feature_indices = indices("feature_indices", fi);
+    if (scaling.count() / 3 != rotation.count() / 4) throw std::runtime_error("scaling / rotation lengths differ");
+    d.scaling = reinterpret_cast<const int8_t *>(scaling.data.data()); d.rotation = reinterpret_cast<const int8_t *>(rotation.data.data());
+    d.num_covars = rotation.count() / 4;
+    // sh degree from features_rest.shape[1] + 1 (io/npz.rs:33-37)
+    const size_t ncoef = rest.shape.size() >= 2 ? rest.shape[1] + 1 : 1;
+    size_t root = 0; while (root * root < ncoef) root++;
+    if (root * root != ncoef || root == 0 || root > 4) throw std::runtime_error("num sh coefs not valid");
+    d.sh_deg = (uint32_t)root - 1;
+    d.num_features = dc.count() / 3;
+    if (rest.count() != d.num_features * (ncoef - 1) * 3) throw std::runtime_error("features_rest / features_dc lengths differ");
+    d.features_dc = reinterpret_cast<const int8_t *>(dc.data.data()); d.features_rest = reinterpret_cast<const int8_t *>(rest.data.data());
+    d.scaling_scale = (float)scalar_or(m, "scaling_scale", 1.0); d.scaling_zero_point = (int32_t)scalar_or(m, "scaling_zero_point", 0);
+    d.rotation_scale = (float)scalar_or(m, "rotation_scale", 1.0); d.rotation_zero_point = (int32_t)scalar_or(m, "rotation_zero_point", 0);
+    auto quant = [&](ws_quantization &q, const std::string &key, bool present) {
+        q.zero_point = present ? (int32_t)scalar_or(m, key + "_zero_point", 0) : 0;
+        q.scale = present ? (float)scalar_or(m, key + "_scale", 1.0) : 1.f;
+    };
+    quant(d.quantization.color_dc, "features_dc", true); quant(d.quantization.color_rest, "features_rest", true);
+    quant(d.quantization.opacity, "opacity", true); quant(d.quantization.scaling_factor, "scaling_factor", has_sf);
+    if (const npz::Array *a = maybe(m, "mip_splatting")) { d.has_mip_splatting = 1; d.mip_splatting = a->as_double(0) != 0.0; }
+    if (const npz::Array *a = maybe(m, "kernel_size")) { d.has_kernel_size = 1; d.kernel_size = (float)a->as_double(0); }
+    if (const npz::Array *a = maybe(m, "background_color")) {
+        if (a->count() < 3) throw std::runtime_error("background_color needs 3 entries");
+        d.has_background = 1;
+        for (int i = 0; i < 3; i++) d.background_color[i] = (float)a->as_double(i);
+    }
+    return d;
+}
+
+ws::PointCloud pointcloud_from_npz(const ws::Context &ctx, const std::string &file)
+{
+    const std::map<std::string, npz::Array> m = npz::read(reinterpret_cast<const uint8_t *>(file.data()), file.size());
+    std::vector<int32_t> gi, fi;
+    const ws_c3dgs_arrays d = c3dgs_from_members(m, gi, fi);
+    return ws::PointCloud::from_c3dgs(ctx, d);
+}
+
 // ---- PNG (RGBA8, filter 0, stored deflate blocks) -----------------------------------------------------------------------
 uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n)
 {
@@ -205,8 +293,10 @@ void render_views(const ws::Context &ctx, ws::GaussianRenderer &renderer, const 
 
 int usage()
 {
-    std::fprintf(stderr, "usage: ws_render <input.ply> <cameras.json> <img_out> [--max-sh-deg N]\n"
+    std::fprintf(stderr, "usage: ws_render <input.ply|.npz> <cameras.json> <img_out> [--max-sh-deg N]\n"
                          "       ws_render --parse-scene <cameras.json>\n"
+                         "       ws_render --parse-npz <file.npz>\n"
+                         "       ws_render --check-npz <file.npz>\n"
                          "       ws_render --png-selftest <out.png> <width> <height>\n");
     return 64;
 }
@@ -228,6 +318,33 @@ int main(int argc, char **argv)
             }
             return 0;
         }
+        if (argc >= 3 && std::string(argv[1]) == "--parse-npz") {
+            const std::string file = read_file(argv[2]);
+            for (const auto &kv : npz::read(reinterpret_cast<const uint8_t *>(file.data()), file.size())) {
+                uint64_t hsh = 1469598103934665603ull;                              // FNV-1a over the payload
+                for (uint8_t b : kv.second.data) { hsh ^= b; hsh *= 1099511628211ull; }
+                std::printf("%s %s", kv.first.c_str(), kv.second.descr.c_str());
+                for (size_t s_ : kv.second.shape) std::printf(" %zu", s_);
+                std::printf(" | %zu %016llx\n", kv.second.data.size(), (unsigned long long)hsh);
+            }
+            return 0;
+        }
+        if (argc >= 3 && std::string(argv[1]) == "--check-npz") {          // the ws_c3dgs_arrays the loader would hand to the GPU (no GPU)
+            const std::string file = read_file(argv[2]);
+            const std::map<std::string, npz::Array> m = npz::read(reinterpret_cast<const uint8_t *>(file.data()), file.size());
+            std::vector<int32_t> gi, fi;
+            const ws_c3dgs_arrays d = c3dgs_from_members(m, gi, fi);
+            std::printf("points %llu covars %llu features %llu sh_deg %u scaling_factor %d gaussian_indices %d feature_indices %d\n",
+                        (unsigned long long)d.num_points, (unsigned long long)d.num_covars, (unsigned long long)d.num_features, d.sh_deg,
+                        d.scaling_factor != nullptr, d.gaussian_indices != nullptr, d.feature_indices != nullptr);
+            std::printf("scaling %.9g %d rotation %.9g %d\n", d.scaling_scale, d.scaling_zero_point, d.rotation_scale, d.rotation_zero_point);
+            const ws_quantization *q[4] = {&d.quantization.color_dc, &d.quantization.color_rest, &d.quantization.opacity, &d.quantization.scaling_factor};
+            for (int i = 0; i < 4; i++) std::printf("quant %d %.9g\n", q[i]->zero_point, q[i]->scale);
+            std::printf("meta mip %d %d kernel %d %.9g bg %d %.9g %.9g %.9g\n", d.has_mip_splatting, d.mip_splatting, d.has_kernel_size, d.kernel_size,
+                        d.has_background, d.background_color[0], d.background_color[1], d.background_color[2]);
+            if (d.gaussian_indices && d.num_points) std::printf("gi0 %d gilast %d\n", d.gaussian_indices[0], d.gaussian_indices[d.num_points - 1]);
+            return 0;
+        }
         if (argc >= 5 && std::string(argv[1]) == "--png-selftest") {
             const uint32_t w = (uint32_t)std::atoi(argv[3]), h = (uint32_t)std::atoi(argv[4]);
             std::vector<uint16_t> frame((size_t)w * h * 4);
@@ -244,9 +361,11 @@ int main(int argc, char **argv)
         const ws::Scene scene = scene_from_json(read_file(argv[2]));
         std::printf("reading point cloud file '%s'\n", argv[1]);
         const std::string file = read_file(argv[1]);
-        if (file.compare(0, 3, "ply") != 0) throw std::runtime_error("Unknown file format (this tool reads .ply; see the header comment for .npz)");
+        // GenericGaussianPointCloud::load (io/mod.rs:44-61): dispatch on the magic bytes
+        const bool is_ply = file.compare(0, 3, "ply") == 0, is_npz = file.compare(0, 4, "PK\x03\x04") == 0;
+        if (!is_ply && !is_npz) throw std::runtime_error("Unknown file format");
         ws::Context ctx(0);
-        ws::PointCloud pc = ws::PointCloud::from_ply(ctx, file.data(), file.size());
+        ws::PointCloud pc = is_ply ? ws::PointCloud::from_ply(ctx, file.data(), file.size()) : pointcloud_from_npz(ctx, file);
         ws::GaussianRenderer renderer = ws::GaussianRenderer::new_(ctx, WS_FORMAT_RGBA16_FLOAT, pc.sh_deg(), pc.compressed());
         render_views(ctx, renderer, pc, scene.cameras(ws::Split::Test), argv[3], "test");
         render_views(ctx, renderer, pc, scene.cameras(ws::Split::Train), argv[3], "train");

@@ -89,13 +89,16 @@ def build_tools(force=False):
     """tools/ws_render.cpp: the offline dataset renderer in C++ on top of the C ABI (header-only mirror include/websplat_b200.hpp)."""
     src = os.path.join(TOOLS_DIR, "ws_render.cpp")
     inc = os.path.normpath(os.path.join(HERE, "..", "include"))
-    deps = [src, os.path.join(inc, "websplat_b200.hpp"), os.path.join(inc, "websplat_b200.h"), OUT]
+    deps = [src, os.path.join(TOOLS_DIR, "npz_reader.hpp"), os.path.join(inc, "websplat_b200.hpp"), os.path.join(inc, "websplat_b200.h"), OUT]
     if not os.path.exists(src):
         return None
     if force or _stale(TOOL_OUT, deps):
         cxx = os.environ.get("CXX") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++")
+        have_zlib = any(os.path.exists(os.path.join(d, "zlib.h")) for d in ("/usr/include", "/usr/local/include"))
         cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", TOOL_OUT, src, "-L" + HERE, "-lwebsplat_b200",
                "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread", "-lrt"]
+        if have_zlib:                      # deflated .npz members (np.savez_compressed); stored ones need nothing
+            cmd += ["-DWS_HAVE_ZLIB", "-lz"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             sys.stderr.write(p.stdout + p.stderr)
