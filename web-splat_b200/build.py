@@ -77,7 +77,10 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(p.stdout + p.stderr)
             raise RuntimeError("link failed")
-    build_tools(force=force)
+    try:                                   # the C++ tool is auxiliary: the library must not depend on it
+        build_tools(force=force)
+    except Exception as e:                 # noqa: BLE001
+        sys.stderr.write("websplat_b200: tools/ws_render.cpp was not built: %s\n" % e)
     return OUT, logs
 
 
