@@ -160,3 +160,27 @@ def test_cpp_npz_reader_matches_numpy(ws, tool, tmp_path, compressed_zip):
     assert r.returncode == 1 and "rotation" in r.stderr
     path4 = tmp_path / "f.npz"; path4.write_bytes(path.read_bytes()[:-30])
     assert subprocess.run([tool, "--parse-npz", str(path4)], capture_output=True, text=True).returncode == 1
+
+
+def test_cpp_readers_survive_damaged_input(ws, tool, tmp_path):
+    """the zip / npy / JSON readers of the C++ tool on damaged files: an error exit is fine, a crash (signal) is not."""
+    rng = np.random.default_rng(11)
+    a = ws.synth.c3dgs_arrays(40, 4, 1, codebook=8)
+    src = tmp_path / "g.npz"; np.savez_compressed(src, **a)
+    good = src.read_bytes()
+    cams = json.dumps(_scene_entries(ws, 3, 320, 200)).encode()
+    victim = tmp_path / "v.bin"
+    for i in range(240):
+        base, flag = (good, "--check-npz") if i % 2 == 0 else (cams, "--parse-scene")
+        b = bytearray(base)
+        k = rng.integers(0, 3)
+        if k == 0:
+            for _ in range(rng.integers(1, 8)):
+                b[rng.integers(0, len(b))] = rng.integers(0, 256)
+        elif k == 1:
+            b = b[:rng.integers(0, len(b))]
+        else:
+            j = rng.integers(0, len(b)); del b[j:j + rng.integers(1, 64)]
+        victim.write_bytes(bytes(b))
+        p = subprocess.run([tool, flag, str(victim)], capture_output=True, timeout=60)
+        assert p.returncode in (0, 1), (flag, p.returncode, p.stderr[-200:])
