@@ -73,6 +73,9 @@ def lib():
                                         C.c_float, C.c_int32, C.c_float, C.c_int32, vp, vp, vp, vp, vp, vp]
         L.wso_tile_rects.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(C.c_uint64)]
         L.wso_num_threads.restype = C.c_int
+        L.wso_set_num_threads.restype = None; L.wso_set_num_threads.argtypes = [C.c_int]
+        L.wso_composite_rop.restype = None
+        L.wso_composite_rop.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -91,6 +94,19 @@ def f16_bits_to_f32(h):
 
 def num_threads():
     return lib().wso_num_threads()
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1: bench.py sets the count itself)."""
+    lib().wso_set_num_threads(int(n))
+
+
+def host_cores():
+    """Cores this process may run on (cgroup / affinity aware)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def aabb_radius(bmin, bmax):
@@ -174,6 +190,16 @@ def composite(splats, order, W, H, clear=(0, 0, 0, 0), want_sens=False):
     clr = np.ascontiguousarray(clear, np.float32)
     lib().wso_composite(_p(splats), _p(order), order.size, W, H, _p(clr), _p(out), _p(sens) if want_sens else None)
     return (out, sens) if want_sens else out
+
+
+def composite_rop(splats, order, W, H, fmt, clear=(0, 0, 0, 0)):
+    """Stage 3 as the reference's render target would hold it: the blend result is rounded to the target format
+    (fmt 0 = Rgba8Unorm, 1 = Rgba16Float, 2 = Rgba32Float) after EVERY layer (renderer.rs:63-67).  f32 [H,W,4]."""
+    splats = np.ascontiguousarray(splats, np.uint16); order = np.ascontiguousarray(order, np.uint32)
+    out = np.empty((H, W, 4), np.float32)
+    clr = np.ascontiguousarray(clear, np.float32)
+    lib().wso_composite_rop(_p(splats), _p(order), order.size, W, H, _p(clr), int(fmt), _p(out))
+    return out
 
 
 def tile_rects(splats, W, H):

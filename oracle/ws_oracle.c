@@ -594,8 +594,24 @@ static void decode_splat(const uint16_t *h, uint32_t W, uint32_t H, splat_dec *s
  * sens (optional, W*H f32): per pixel, an upper bound on how much the result could
  * change if a test `a > 2*CUTOFF` within +-1e-4 of the threshold flipped.
  */
-WSO_API void wso_composite(const uint16_t *splats, const uint32_t *order, uint32_t V,
-                           uint32_t W, uint32_t H, const float clear[4], float *out, float *sens)
+/* rounding of one blended channel to the render target's storage format, as the ROP does after EVERY blend
+ * (renderer.rs:63-67 blends in the target: Rgba8Unorm lib.rs:192-196 / measure.rs:184, Rgba16Float render.rs:154,
+ * Rgba32Float video.rs:186).  rop < 0: no per-blend rounding (f32 accumulator, the parity oracle of the float
+ * compositor).  Unorm8: saturate, scale by 255, round half to even (Vulkan/D3D float->UNORM conversion). */
+static inline float rop_round(float x, int rop)
+{
+    if (rop == 0) {
+        float c = (x > 0.f) ? x : 0.f;              /* NaN -> 0 */
+        if (c > 1.f) c = 1.f;
+        float q = nearbyintf(c * 255.f);            /* default rounding mode = RNE */
+        return q / 255.f;
+    }
+    if (rop == 1) return wso_f16_to_f32(wso_f32_to_f16(x));
+    return x;
+}
+
+static void composite_impl(const uint16_t *splats, const uint32_t *order, uint32_t V,
+                           uint32_t W, uint32_t H, const float clear[4], float *out, float *sens, int rop)
 {
     const uint32_t BAND = 16;
     uint32_t nb = (H + BAND - 1) / BAND;
@@ -631,7 +647,7 @@ WSO_API void wso_composite(const uint16_t *splats, const uint32_t *order, uint32
         for (uint32_t y = ry0; y < ry1; y++)
             for (uint32_t x = 0; x < W; x++) {
                 float *d = out + ((size_t)y * W + x) * 4u;
-                d[0] = clear[0]; d[1] = clear[1]; d[2] = clear[2]; d[3] = clear[3];
+                d[0] = rop_round(clear[0], rop); d[1] = rop_round(clear[1], rop); d[2] = rop_round(clear[2], rop); d[3] = rop_round(clear[3], rop);
                 if (sens) sens[(size_t)y * W + x] = 0.f;
             }
         for (size_t li = cnt[b]; li < cnt[b + 1]; li++) {
@@ -669,15 +685,35 @@ WSO_API void wso_composite(const uint16_t *splats, const uint32_t *order, uint32
                     float bb = (float)bd;
                     float *d = out + ((size_t)y * W + x) * 4u;
                     float om = 1.f - bb;
-                    d[0] = s->rgba[0] * bb + d[0] * om;      /* src + dst*(1-src.a), renderer.rs:63-67 */
-                    d[1] = s->rgba[1] * bb + d[1] * om;
-                    d[2] = s->rgba[2] * bb + d[2] * om;
-                    d[3] = bb + d[3] * om;
+                    d[0] = rop_round(s->rgba[0] * bb + d[0] * om, rop);      /* src + dst*(1-src.a), renderer.rs:63-67 */
+                    d[1] = rop_round(s->rgba[1] * bb + d[1] * om, rop);
+                    d[2] = rop_round(s->rgba[2] * bb + d[2] * om, rop);
+                    d[3] = rop_round(bb + d[3] * om, rop);
                 }
             }
         }
     }
     free(fill); free(list); free(cnt); free(y1s); free(y0s); free(dec);
+}
+
+WSO_API void wso_composite(const uint16_t *splats, const uint32_t *order, uint32_t V,
+                           uint32_t W, uint32_t H, const float clear[4], float *out, float *sens)
+{
+    composite_impl(splats, order, V, W, H, clear, out, sens, -1);
+}
+
+/*
+ * ROP-faithful variant: identical walk, but the destination holds what the reference's render target would hold --
+ * every blend result is rounded to the target format (format: 0 = Rgba8Unorm, 1 = Rgba16Float, 2 = Rgba32Float)
+ * before the next layer reads it back.  The blend arithmetic itself is f32 (the fixed-function blender's internal
+ * precision is not specified by Vulkan; f32 + one rounding to the target is the common hardware behaviour).
+ * out: W*H*4 f32 holding the quantised values.  Used to MEASURE how far a float compositor (this repo's CUDA
+ * path, or wso_composite) is from the reference's own target contents (tests/test_oracle.py).
+ */
+WSO_API void wso_composite_rop(const uint16_t *splats, const uint32_t *order, uint32_t V,
+                               uint32_t W, uint32_t H, const float clear[4], int format, float *out)
+{
+    composite_impl(splats, order, V, W, H, clear, out, NULL, format);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -886,6 +922,16 @@ WSO_API int wso_num_threads(void)
     return omp_get_max_threads();
 #else
     return 1;
+#endif
+}
+
+/* bench.py sets the thread count itself (torchrun exports OMP_NUM_THREADS=1 to every rank) */
+WSO_API void wso_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
 #endif
 }
 

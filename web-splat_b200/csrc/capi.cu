@@ -984,6 +984,8 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
             a.status = r->d_status_tile + (set_off + (size_t)p * sparts_p) * 256;
             a.gstatus = r->d_gstatus_tile + (gset_off + (size_t)p * gparts_p) * 256;
             a.ranges = (p == r->tile_passes - 1) ? r->d_ranges + (half ? r->tiles_cap : 0) : nullptr;   // the last pass also emits the tile ranges
+            // ... and nothing downstream reads the sorted tile ids (the compositor walks values + ranges): drop that store
+            if (a.ranges && sort_pass_can_skip_keys()) a.keys_out = nullptr;
             a.ticket = &r->d_counters->ticket[(half ? TK_TSORT_FAR : TK_TSORT) + p];
             a.hist = r->d_hist_tile + half * 4 * 256 + p * 256;
             a.shift = 8u * (uint32_t)p;
@@ -1571,6 +1573,19 @@ extern "C" ws_status ws_renderer_read_buffer(ws_renderer *r, ws_buffer_id which,
         }
         uint32_t *o = static_cast<uint32_t *>(dst);
         for (size_t i = 0; i < V; i++) if (si[i] < V) o[si[i]] = sk[i];
+        return WS_OK;
+    }
+    if (which == WS_BUF_PAIR_TILES && sort_pass_can_skip_keys()) {
+        // the last tile pass does not store the sorted tile ids (nothing on the frame path reads them);
+        // the sorted list is "tile t repeated over [begin_t, end_t)", rebuilt here from the ranges
+        std::vector<uint32_t> rg(2 * T);
+        if (T) CU(cudaMemcpy(rg.data(), r->d_ranges + (r->frame_split ? r->tiles_cap : 0), T * 8, cudaMemcpyDeviceToHost));
+        uint32_t *o = static_cast<uint32_t *>(dst);
+        for (size_t i = 0; i < P; i++) o[i] = 0xffffffffu;
+        for (size_t t = 0; t < T; t++) {
+            const uint32_t b = rg[2 * t], e = ~rg[2 * t + 1];
+            if (e > b) for (size_t i = b; i < e && i < P; i++) o[i] = (uint32_t)t;
+        }
         return WS_OK;
     }
     if (bytes) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));

@@ -282,6 +282,231 @@ onesweep_pass_kernel(SortPassArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// V2 of the pass (default): what ncu named on V1 (r01m/r01q: SM 30-37 %, short_scoreboard 28-33 % + long_scoreboard
+// 20-25 %, ~38 shared-memory wavefront cycles per warp-item on random digits) is attacked three ways:
+//   * TMA staging: the NEXT partition's keys and values (2 x 16 KB) are fetched by cp.async.bulk (UBLKCP) into a
+//     staging buffer while the current partition is in its look-back and write-out; the ticket of the next partition
+//     is taken at the top of the iteration, so neither the ticket round trip nor the two global-load latencies sit
+//     on the per-partition critical path any more.  Values never pass through registers (80 -> ~56 registers);
+//   * ranking on packed {peer mask, running count} 64-bit words: one atomicOr, one LDS.64 and one STS.64 by the
+//     lowest peer per item (V1: atomicOr + two LDS + atomicAdd + STS);
+//   * the reorder reads ONE table entry (bin start + warp prefix, merged after the per-bin scan) and writes ONE
+//     64-bit {key, value} word; the write-out reads it back with one LDS.64.
+// Also: a pass whose digit is the same for every key (one histogram bin holds all n keys -- the top byte of the
+// compressed layout's 24-bit key) degenerates to a plain copy, and the last tile pass may skip the key store
+// (keys_out == NULL: the compositor only needs the values and the tile ranges).
+struct SortSmemV2 {
+    uint32_t stage_k[SORT_PART];              // TMA destination: next partition's keys ...
+    uint32_t stage_v[SORT_PART];              // ... and values
+    uint2 kv[SORT_PART];                      // reorder buffer; its first 16 KB hold the {mask, count} words while ranking
+    uint32_t tbl[WARPS][256];                 // first local position of (warp, bin) in the partition
+    uint32_t gbase[256];
+    uint32_t scan[WARPS];
+    uint32_t part;
+    uint64_t bar;
+};
+
+template <bool EMIT_RANGES>
+__global__ void __launch_bounds__(SORT_THREADS, 3)
+onesweep_pass_v2_kernel(SortPassArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SortSmemV2 &S = *reinterpret_cast<SortSmemV2 *>(smem_raw);
+    static_assert(WARPS * 256 * sizeof(uint2) <= sizeof(S.kv), "rank words must fit in the reorder buffer");
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t n = *a.n_ptr;
+    if (n > a.n_cap) n = a.n_cap;
+    const uint32_t nparts = (n + SORT_PART - 1u) / SORT_PART;
+    const uint32_t shift = a.shift;
+    const bool use_tma = ((reinterpret_cast<uintptr_t>(a.keys_in) | reinterpret_cast<uintptr_t>(a.vals_in)) & 15u) == 0u;
+
+    // exclusive scan of the global digit histogram (thread tid owns bin tid) + "every key has the same digit"
+    uint32_t g_excl;
+    {
+        const uint32_t c = a.hist[tid];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) S.scan[warp] = incl;
+        if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+        const int ident = __syncthreads_or((n > 0u && c == n) ? 1 : 0);
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) if (w < (int)warp) woff += S.scan[w];
+        g_excl = woff + incl - c;
+        if (ident) {
+            // identity permutation: stream the pairs through (grid-stride, no ranking, no look-back)
+            for (uint32_t i = blockIdx.x * SORT_THREADS + tid; i < n; i += gridDim.x * SORT_THREADS) {
+                const uint32_t kk = a.keys_in[i];
+                if (a.keys_out) a.keys_out[i] = kk;
+                a.vals_out[i] = a.vals_in[i];
+                if (EMIT_RANGES) {
+                    const bool first = (i == 0u) || (a.keys_in[i - 1u] != kk);
+                    const bool last = (i == n - 1u) || (a.keys_in[i + 1u] != kk);
+                    if (first) atomicMin(&a.ranges[kk].x, i);
+                    if (last) atomicMin(&a.ranges[kk].y, ~(i + 1u));
+                }
+            }
+            return;
+        }
+    }
+
+    auto issue = [&](uint32_t part) {                 // thread 0: stage a FULL partition through the TMA engine
+        fence_proxy_async();                          // earlier generic-proxy reads of the stage happen-before the async writes
+        mbar_arrive_expect_tx(&S.bar, 2u * SORT_PART * 4u);
+        bulk_g2s(S.stage_k, a.keys_in + (size_t)part * SORT_PART, SORT_PART * 4u, &S.bar);
+        bulk_g2s(S.stage_v, a.vals_in + (size_t)part * SORT_PART, SORT_PART * 4u, &S.bar);
+    };
+    auto is_full = [&](uint32_t part) { return part < nparts && (n - part * SORT_PART) >= (uint32_t)SORT_PART; };
+
+    if (tid == 0) {
+        const uint32_t p0 = atomicAdd(a.ticket, 1u);
+        S.part = p0;
+        if (use_tma && is_full(p0)) issue(p0);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (;;) {
+        const uint32_t part = S.part;
+        if (part >= nparts) break;
+        const uint32_t base = part * SORT_PART;
+        const uint32_t nvalid = (n - base < (uint32_t)SORT_PART) ? (n - base) : (uint32_t)SORT_PART;
+        const bool full = nvalid == (uint32_t)SORT_PART;
+        uint32_t next_ticket = 0;
+        if (tid == 0) next_ticket = atomicAdd(a.ticket, 1u);          // consumed after the reorder: the round trip is hidden
+
+        const uint32_t wbase = warp * (32u * SORT_ITEMS);
+        if (use_tma && full) {
+            mbar_wait(&S.bar, phase); phase ^= 1u;
+        } else {                                                       // ragged tail (or unaligned caller buffers): plain loads
+#pragma unroll
+            for (int i = 0; i < SORT_ITEMS; i++) {
+                const uint32_t li = wbase + i * 32u + lane;
+                S.stage_k[li] = (li < nvalid) ? a.keys_in[base + li] : 0xffffffffu;   // pads rank last (radix_sort.wgsl:79)
+                S.stage_v[li] = (li < nvalid) ? a.vals_in[base + li] : 0u;
+            }
+            __syncwarp();                                              // each warp reads back only what it wrote
+        }
+        // keys, warp-striped: warp w owns [w*512, +512), item i of lane l = i*32 + l
+        uint32_t key[SORT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) key[i] = S.stage_k[wbase + i * 32u + lane];
+        {   // clear the {mask, count} words: 16 KB = 4 x uint4 per thread
+            uint4 *z = reinterpret_cast<uint4 *>(S.kv);
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < (WARPS * 256 * 8) / (16 * SORT_THREADS); i++) z[i * SORT_THREADS + tid] = z4;
+        }
+        __syncthreads();
+
+        // ---- rank inside the warp on packed words {x: peer mask of the current round, y: keys of this digit seen so far}
+        uint32_t rank2[SORT_ITEMS / 2];
+        {
+            uint2 *wt = S.kv + warp * 256u;
+            const uint32_t lanebit = 1u << lane, lower = lanebit - 1u;
+#pragma unroll
+            for (int i = 0; i < SORT_ITEMS; i++) {
+                const uint32_t d = (key[i] >> shift) & 255u;
+                atomicOr(&wt[d].x, lanebit);
+                __syncwarp();
+                const uint2 mc = wt[d];
+                const uint32_t rk = mc.y + (uint32_t)__popc(mc.x & lower);
+                __syncwarp();                                          // every peer has read the word
+                if ((mc.x & lower) == 0u) wt[d] = make_uint2(0u, mc.y + (uint32_t)__popc(mc.x));   // lowest peer: advance, clear
+                __syncwarp();
+                if (i & 1) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
+            }
+        }
+        __syncthreads();
+
+        // ---- per bin (thread tid = bin): totals over the warps, publish the partition's aggregate
+        uint32_t cw[WARPS];
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) { cw[w] = S.kv[w * 256u + tid].y; total += cw[w]; }
+        uint32_t *st = a.status + (size_t)part * 256u + tid;
+        st_relaxed(st, (part == 0u ? LB_PREFIX : LB_AGGREGATE) | total);
+        uint32_t binstart;
+        {
+            uint32_t incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            if (lane == 31) S.scan[warp] = incl;
+            __syncthreads();                                           // also: every thread has read its rank words out of S.kv
+            uint32_t woff = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) if (w < (int)warp) woff += S.scan[w];
+            binstart = woff + incl - total;
+        }
+        {
+            uint32_t run = binstart;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { S.tbl[w][tid] = run; run += cw[w]; }
+        }
+        __syncthreads();
+
+        // ---- reorder in shared memory: one table read, one 64-bit {key, value} store per item
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            const uint32_t d = (key[i] >> shift) & 255u;
+            const uint32_t pos = S.tbl[warp][d] + ((rank2[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+            S.kv[pos] = make_uint2(key[i], S.stage_v[wbase + i * 32u + lane]);
+        }
+        __syncthreads();                                               // the stage is free again
+        if (tid == 0) {
+            S.part = next_ticket;
+            if (use_tma && is_full(next_ticket)) issue(next_ticket);   // in flight during the look-back and the write-out
+        }
+
+        // ---- two-level decoupled look-back
+        LbState lb; lb.excl = 0; lb.done = (part == 0u);
+        {
+            const uint32_t grp = part / SORT_LB_GROUP;
+            const bool leader = (part % SORT_LB_GROUP) == SORT_LB_GROUP - 1u;
+            lookback_level(a.status + tid, (int)part - 1, (int)(grp * SORT_LB_GROUP), grp == 0u, lb, a.err);
+            uint32_t *gst = a.gstatus + (size_t)grp * 256u + tid;
+            if (leader) st_relaxed(gst, (lb.done ? LB_PREFIX : LB_AGGREGATE) | ((lb.excl + total) & LB_VALUE_MASK));
+            if (!lb.done) {
+                lookback_level(a.gstatus + tid, (int)grp - 1, 0, true, lb, a.err);
+                if (leader) st_relaxed(gst, LB_PREFIX | ((lb.excl + total) & LB_VALUE_MASK));
+            }
+            if (part > 0u) st_relaxed(st, LB_PREFIX | ((lb.excl + total) & LB_VALUE_MASK));
+        }
+        S.gbase[tid] = g_excl + lb.excl - binstart;                    // wraps mod 2^32 by design
+        __syncthreads();
+
+        // ---- write out: consecutive threads write consecutive addresses within a bin run
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; k++) {
+            const uint32_t i = tid + k * SORT_THREADS;
+            if (i < nvalid) {
+                const uint2 p = S.kv[i];
+                const uint32_t kk = p.x;
+                const uint32_t g = S.gbase[(kk >> shift) & 255u] + i;
+                if (a.keys_out) a.keys_out[g] = kk;
+                a.vals_out[g] = p.y;
+                if (EMIT_RANGES) {                                     // see V1: run boundaries via atomicMin
+                    const bool first = (i == 0u) || (S.kv[i - 1u].x != kk);
+                    const bool last = (i == nvalid - 1u) || (S.kv[i + 1u].x != kk);
+                    if (first) atomicMin(&a.ranges[kk].x, g);
+                    if (last) atomicMin(&a.ranges[kk].y, ~(g + 1u));
+                }
+            }
+        }
+        __syncthreads();                                               // S.kv is free; S.part (next partition) is visible
+    }
+}
+
 // Standalone digit histograms (only for the public ws_sort_pairs_u32 entry point; the frame
 // path gets its histograms from preprocess / binning).
 __global__ void __launch_bounds__(256)
@@ -317,8 +542,42 @@ static int rank_ways()
     return ways;
 }
 
+static int sort_variant()
+{
+    static int v = [] {
+        const char *e = getenv("WS_SORT_VARIANT");           // 2 = TMA-staged pass (default), 1 = the round-1 pass (kept for A/B in profiles/)
+        const int w = e ? atoi(e) : 2;
+        return (w == 1) ? 1 : 2;
+    }();
+    return v;
+}
+
+constexpr size_t SORT_V2_SMEM = sizeof(SortSmemV2) + 128;    // + slack for the 128-B alignment of the TMA destination
+
+// the opt-in above 48 KB of dynamic shared memory is per device (several contexts may live in one process)
+static cudaError_t sort_v2_prepare()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(onesweep_pass_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_V2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_V2_SMEM);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
 cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t stream)
 {
+    if (sort_variant() == 2) {
+        cudaError_t e = sort_v2_prepare();
+        if (e != cudaSuccess) return e;
+        if (a.ranges) onesweep_pass_v2_kernel<true><<<grid, SORT_THREADS, SORT_V2_SMEM, stream>>>(a);
+        else onesweep_pass_v2_kernel<false><<<grid, SORT_THREADS, SORT_V2_SMEM, stream>>>(a);
+        return cudaGetLastError();
+    }
+    if (!a.keys_out) return cudaErrorInvalidValue;           // only the V2 pass can drop the key store
     const int w = rank_ways();
 #define WS_LAUNCH(R, W) onesweep_pass_kernel<R, W><<<grid, SORT_THREADS, 0, stream>>>(a)
     if (a.ranges) { if (w == 4) WS_LAUNCH(true, 4); else if (w == 2) WS_LAUNCH(true, 2); else WS_LAUNCH(true, 1); }
@@ -327,18 +586,25 @@ cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t strea
     return cudaGetLastError();
 }
 
+bool sort_pass_can_skip_keys() { return sort_variant() == 2; }
+
 int sort_pass_blocks_per_sm()
 {
     int best = 1 << 30;
-    auto probe = [&](auto kernel) {
+    auto probe = [&](auto kernel, size_t smem) {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, SORT_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, SORT_THREADS, smem);
         if (nb < best) best = nb;
     };
-    const int w = rank_ways();
-    if (w == 4) { probe(onesweep_pass_kernel<false, 4>); probe(onesweep_pass_kernel<true, 4>); }
-    else if (w == 2) { probe(onesweep_pass_kernel<false, 2>); probe(onesweep_pass_kernel<true, 2>); }
-    else { probe(onesweep_pass_kernel<false, 1>); probe(onesweep_pass_kernel<true, 1>); }
+    if (sort_variant() == 2) {
+        if (sort_v2_prepare() != cudaSuccess) return 1;
+        probe(onesweep_pass_v2_kernel<false>, SORT_V2_SMEM); probe(onesweep_pass_v2_kernel<true>, SORT_V2_SMEM);
+    } else {
+        const int w = rank_ways();
+        if (w == 4) { probe(onesweep_pass_kernel<false, 4>, 0); probe(onesweep_pass_kernel<true, 4>, 0); }
+        else if (w == 2) { probe(onesweep_pass_kernel<false, 2>, 0); probe(onesweep_pass_kernel<true, 2>, 0); }
+        else { probe(onesweep_pass_kernel<false, 1>, 0); probe(onesweep_pass_kernel<true, 1>, 0); }
+    }
     return best > 0 && best < (1 << 30) ? best : 1;
 }
 

@@ -36,7 +36,7 @@ constexpr unsigned SORT_LB_GROUP = 16;                 // partitions per look-ba
 
 struct SortPassArgs {
     const uint32_t *keys_in, *vals_in;
-    uint32_t *keys_out, *vals_out;
+    uint32_t *keys_out, *vals_out;   // keys_out may be NULL on the last tile pass (see sort_pass_can_skip_keys)
     const uint32_t *n_ptr;        // device: number of pairs (clamped to n_cap)
     uint32_t n_cap;
     uint32_t *status;             // [ceil(n_cap/4096)][256] look-back words, zeroed before the pass
@@ -49,6 +49,7 @@ struct SortPassArgs {
 };
 cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t stream);
 int sort_pass_blocks_per_sm();
+bool sort_pass_can_skip_keys();   // the default (TMA-staged) pass accepts keys_out == NULL: the last tile pass then drops the key store
 // digit histograms of up to 4 passes (shift 0,8,16,24) in one sweep over the keys; hist zeroed by caller
 cudaError_t launch_sort_histogram(const uint32_t *keys, const uint32_t *n_ptr, uint32_t n_cap,
                                   uint32_t *hist /*4x256*/, int passes, int grid, cudaStream_t stream);
