@@ -100,6 +100,26 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def frame_crc(host):
+    """CRC-32 of EVERY byte of a downloaded frame (pinned host tensor or numpy array): the parity evidence the bench
+    lines carry -- the same view must give the same value at 1, 2, 4 and 8 GPUs and with the occlusion split on or off."""
+    import zlib
+    a = host if isinstance(host, np.ndarray) else host.view(__import__("torch").uint8).numpy()
+    return "%08x" % (zlib.crc32(a.tobytes()) & 0xffffffff)
+
+
+CHECKSUM_VIEW = 0                           # index into the workload's camera list
+
+
+def host_threads():
+    """host cores this process may use (affinity / cgroup aware); the oracle legs set their OpenMP count from it --
+    torchrun exports OMP_NUM_THREADS=1 to every rank, which would otherwise shrink the reference arm to one core"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def make_workload(name):
     import websplat_b200 as ws
     n, W, H, seed, compressed = ws.synth.CONFIGS[name]
@@ -138,6 +158,7 @@ def oracle_frame_seconds(cloud, view, W, H, repeats=1):
     """One full frame of the CPU oracle (stage 1 -> stable u32 sort -> back-to-front composite)."""
     import websplat_b200 as ws
     from oracle import oracle as orc
+    orc.set_num_threads(host_threads())
     fovx, fovy = ws.synth.fov_for_viewport(W, H)
     best = None
     for _ in range(repeats):
@@ -156,6 +177,7 @@ def run_reference(args):
     cloud, W, H, views = make_workload(args.workload)
     from oracle import oracle as orc
     orc.build()
+    orc.set_num_threads(host_threads())
     # The driver launches this arm with the GPU arm's --steps / --warmup (hundreds of steps); a CPU frame of cfg3 takes
     # seconds.  The sample is therefore bounded: at most 3 warm-up frames, then as many FULL frames of the orbit as fit
     # REFERENCE_BUDGET_S (never fewer than 1, never more than --steps); `steps` reports the frames actually timed.
@@ -308,7 +330,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_fps = K / e2e_s
-    checksum = float(host[(Wu + K - 1) % nb][::97, ::89].float().sum())
+
+    # ---- parity evidence in the line: CRC-32 of the full downloaded frame of one fixed view, rendered through the
+    #      product default (occlusion split automatic) and through a renderer with the split off; the multi-GPU arm
+    #      prints the CRC of the same view, so identical values across the N = 1, 2, 4, 8 lines mean identical frames
+    cview = fargs[CHECKSUM_VIEW % len(fargs)]
+    rs[0].prepare(streams[0], pc, cview)
+    rs[0].render_to_host(host[0], pc, stream=streams[0])
+    torch.cuda.synchronize()
+    checksum = frame_crc(host[0])
+    r_off = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
+    r_off.set_pair_capacity(pair_cap)
+    r_off.set_timing(False)
+    r_off.set_occlusion_split(False)
+    r_off.prepare(streams[0], pc, cview)
+    r_off.render_to_host(host[1], pc, stream=streams[0])
+    torch.cuda.synchronize()
+    checksum_off = frame_crc(host[1])
+    # the complete pair list (what a one-pass frame sorts and stages) over the timed views: prices `frac_full_pairs`
+    p_full = []
+    for i in range(min(K, len(fargs))):
+        r_off.prepare(streams[0], pc, fargs[(Wu + i) % len(fargs)])
+        p_full.append(r_off.stats()["num_pairs"])
+    P_full = float(np.mean(p_full))
+    del r_off
 
     # ---- per-stage CUDA-event breakdown over the same views (timing on: 8 event records per frame)
     r.set_timing(True)
@@ -334,15 +379,23 @@ def run_ours(args):
     def gbs(nbytes, ms):
         return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
 
+    bpp = 8                                            # rgba16float
+    # algorithmic bytes per SURVEY.md 8(d), nothing else: in particular NOT the occlusion split's own state round trip
+    # (W*H*32 B) nor the far slab's second sweep over slots + rectangles -- those are costs of this design, not work
+    # the path requires.  P = pairs actually emitted; `frac_full_pairs` prices the same time at the complete pair list.
     kernels = {
         "preprocess": {"ms": acc["ms_preprocess"], "bytes": acc["bytes_preprocess"]},
         "depth_sort_pass": {"ms": acc["ms_depth_sort"] / depth_passes, "bytes": V * 16, "launches": depth_passes},
-        "binning": {"ms": acc["ms_binning"], "bytes": V * 12 + P * 8},
-        "tile_sort_pass": {"ms": acc["ms_tile_sort"] / tile_passes, "bytes": P * 16, "launches": tile_passes},
-        "composite": {"ms": acc["ms_blend"], "bytes": acc["bytes_blend"]},
+        "binning": {"ms": acc["ms_binning"], "bytes": V * 12 + P * 8, "bytes_full_pairs": V * 12 + P_full * 8},
+        "tile_sort_pass": {"ms": acc["ms_tile_sort"] / tile_passes, "bytes": P * 16, "bytes_full_pairs": P_full * 16, "launches": tile_passes},
+        "composite": {"ms": acc["ms_blend"], "bytes": P * 24 + T * 8 + W * H * bpp, "bytes_full_pairs": P_full * 24 + T * 8 + W * H * bpp},
     }
     for kv in kernels.values():
         kv["gbs"] = gbs(kv["bytes"], kv["ms"]); kv["frac"] = kv["gbs"] / peak
+        if "bytes_full_pairs" in kv:
+            kv["frac_full_pairs"] = gbs(kv["bytes_full_pairs"], kv["ms"]) / peak
+    sb_bytes = depth_passes * V * 16 + V * 12 + P * 8 + tile_passes * P * 16 + T * 8 + P * 24 + T * 8 + W * H * bpp
+    sb_bytes_full = depth_passes * V * 16 + V * 12 + P_full * 8 + tile_passes * P_full * 16 + T * 8 + P_full * 24 + T * 8 + W * H * bpp
     dom = max(kernels, key=lambda k_: kernels[k_]["ms"] * kernels[k_].get("launches", 1))
     # DRAM traffic of the dominant kernel (same unit of work as its `bytes`) from the committed ncu --set full captures (cfg3 only)
     traffic, traffic_src = None, None
@@ -359,27 +412,57 @@ def run_ours(args):
             traffic_src = "profiles/kernel_traffic_cfg3.json (ncu --set full, r01m, one-pass frame)"
     except Exception:
         traffic = None
-    clk = (clocks["sm_mhz"] or sm_max) * 1e6
-    evals = P * 256.0                                  # pixel-splat evaluations if every staged splat met every pixel
+    # measured issue / pipe utilisation of the compositor (ncu capture committed under profiles/; None until one exists)
+    pipes, pipes_src = None, None
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "composite_pipes_%s.json" % args.workload)))
+        pipes, pipes_src = pj.get("metrics"), pj.get("source")
+    except Exception:
+        pass
+    sb_ms = acc["ms_sort"] + acc["ms_blend"]
     roofline = {
         "kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
-        "peak_source": peak_src,
+        "frac": kernels[dom]["frac"], "frac_full_pairs": kernels[dom].get("frac_full_pairs"),
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "bytes_formula": "SURVEY.md 8(d): blend = P*(4+20) + T*8 + W*H*B_fmt with P = pairs emitted; no state round trip",
         "note": "stage 3 is FP32/MUFU-issue bound, not HBM bound (SURVEY 8(d)); its HBM fraction is reported because "
-                "the north star asks for it; 'blend_alu' gives pixel-splat evaluations/s against the MUFU ex2 bound",
-        "sort_plus_blend": {"bytes": acc["bytes_sort"] + acc["bytes_blend"], "ms": acc["ms_sort"] + acc["ms_blend"],
-                            "gbs": gbs(acc["bytes_sort"] + acc["bytes_blend"], acc["ms_sort"] + acc["ms_blend"]),
-                            "frac": gbs(acc["bytes_sort"] + acc["bytes_blend"], acc["ms_sort"] + acc["ms_blend"]) / peak},
-        # the same job priced at SURVEY 8(d)'s figures for the north star's 64-bit (tile|depth) LSD sort of P pairs
-        # (152 B per pair + ranges P*8 + T*8 + blend): what that design would have had to move in the time this one takes.
-        # Not a bandwidth claim -- the factored sort moves 0.43x those bytes, which is where its time goes.
-        "sort_plus_blend_at_north_star_bytes": {
-            "bytes": P * 152.0 + P * 8.0 + T * 8.0 + acc["bytes_blend"],
-            "gbs_equivalent": gbs(P * 152.0 + P * 8.0 + T * 8.0 + acc["bytes_blend"], acc["ms_sort"] + acc["ms_blend"]),
-            "frac_equivalent": gbs(P * 152.0 + P * 8.0 + T * 8.0 + acc["bytes_blend"], acc["ms_sort"] + acc["ms_blend"]) / peak},
-        "blend_alu": {"pair_pixel_evals_per_s_upper": evals / (acc["ms_blend"] * 1e-3) if acc["ms_blend"] > 0 else 0.0,
-                      "mufu_peak_per_s": 148 * 16 * clk},
+                "the north star asks for it; 'composite_pipes' holds the measured issue / pipe utilisation (ncu)",
+        "sort_plus_blend": {"bytes": sb_bytes, "ms": sb_ms, "gbs": gbs(sb_bytes, sb_ms), "frac": gbs(sb_bytes, sb_ms) / peak,
+                            "frac_full_pairs": gbs(sb_bytes_full, sb_ms) / peak},
+        "composite_pipes": pipes, "composite_pipes_source": pipes_src,
     }
+
+    # ---- extra lines (not the headline): the reference's `measure` protocol and the CUB yard-stick ---------------
+    extra = {}
+    if not args.no_extra:
+        # bin/measure.rs:34,98,147-153,184: 2048 x 2048, Rgba8Unorm, ONE renderer, 10 samples per camera submitted back
+        # to back, one wait at the end, wall clock (the reference's timer also includes its lazy-init frame; here it does not)
+        try:
+            MW = MH = 2048
+            rm = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA8_UNORM, cloud["sh_deg"], cloud["compressed"])
+            rm.set_pair_capacity(pair_cap); rm.set_timing(False)
+            margs = [frame_args(ws, cloud, v, MW, MH) for v in views]
+            mt = torch.empty((MH, MW, 4), dtype=torch.uint8, device="cuda")
+            for a_ in margs[:3]:
+                rm.prepare(stream, pc, a_); rm.render(mt, pc, stream=stream)
+            torch.cuda.synchronize()
+            samples = 10 if K >= 100 else 1
+            tm = time.perf_counter()
+            for a_ in margs:
+                for _ in range(samples):
+                    rm.prepare(stream, pc, a_); rm.render(mt, pc, stream=stream)
+            torch.cuda.synchronize()
+            dtm = time.perf_counter() - tm
+            extra["measure_equivalent"] = {"frames_per_s": len(margs) * samples / dtm, "viewport": [MW, MH], "target_format": "rgba8unorm",
+                                           "cameras": len(margs), "samples_per_camera": samples, "frames_in_flight": 1,
+                                           "protocol": "bin/measure.rs:34,98,147-153,184 (wall clock, one final wait)"}
+            del rm, mt
+        except Exception as e:                         # never lose the headline to an extra
+            extra["measure_equivalent"] = {"error": str(e)[:200]}
+        try:
+            extra["sort_vs_cub"] = json.load(open(os.path.join(ROOT, "profiles", "r02_sort_vs_cub.json")))
+        except Exception:
+            pass
 
     # ---- CPU baseline: one frame of the same workload on the host cores -------------------------
     cpu = None
@@ -403,7 +486,9 @@ def run_ours(args):
                          "tile_sort": acc["ms_tile_sort"]},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 448, "d2h_bytes_per_step": W * H * 8,
-                "checksum": checksum},
+                "checksum": checksum, "checksum_what": "CRC-32 of the full RGBA16F frame of view %d" % CHECKSUM_VIEW,
+                "checksum_split_off": checksum_off, "checksum_split_identical": checksum == checksum_off},
+        "extra": extra,
         # stage 1 + depth passes + per slab (binning + tile passes + compositor); two slabs with the occlusion split
         "gpu_launches": K * (KERNELS_STAGE1 + depth_passes + (2 if split else 1) * (KERNELS_BINNING + tile_passes + 1)),
         "clocks": clocks,
@@ -421,6 +506,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `measure`-equivalent line (2048^2, RGBA8) under `extra`")
     ap.add_argument("--frames-in-flight", type=int, default=0,
                     help="frames in flight per GPU (one renderer + stream per frame slot); 0 = auto: 2, and 3 at 8 GPUs "
                          "(the smaller the per-GPU share, the more latency-bound a single frame is)")

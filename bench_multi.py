@@ -87,6 +87,40 @@ def run(args):
             for i in range(depth):
                 pipe.frame_peer(fargs[(Wu + i) % len(fargs)])
             sync_all()
+    # ---- parity evidence carried by the line (before anything is timed): the sharded frame of one fixed view, downloaded
+    #      on the root, must have the CRC-32 of the SAME view rendered by ONE GPU (rank 0, plain renderer, whole cloud) --
+    #      and therefore the value bench.py prints at N = 1
+    cview = fargs[bench.CHECKSUM_VIEW % len(fargs)]
+    chk = torch.zeros((H, W, 4), dtype=torch.float16).pin_memory() if rank == 0 else None
+    pipe.synchronize()
+    sync_all()
+    sh.frame_peer(cview, host=chk)
+    sync_all()
+    checksum = checksum_n1 = None
+    if rank == 0:
+        checksum = bench.frame_crc(chk)
+        if args.workload == "cfg5":
+            # cfg5 exists only sharded; the union of the ranks' shards IS the cloud (24 M fits one B200): rebuild it here
+            parts = [shard if q == 0 else ws.synth.make_cloud((n_all * (q + 1)) // world - (n_all * q) // world, seed + 7919 * q, density_n=n_all)
+                     for q in range(world)]
+            full = dict(cloud, gaussians=np.concatenate([p_["gaussians"] for p_ in parts]),
+                        sh_coefs=np.concatenate([p_["sh_coefs"] for p_ in parts]), num_points=n_all)
+            del parts
+        else:
+            full = cloud
+        fgen = ws.GenericGaussianPointCloud(full["gaussians"], full["sh_coefs"], full["sh_deg"], full["num_points"],
+                                            ws.Aabb(cloud["aabb_min"], cloud["aabb_max"]), cloud["center"], compressed=cloud["compressed"],
+                                            covars=cloud.get("covars"), quantization=cloud.get("quantization"))
+        fpc = ws.PointCloud.new(ctx, fgen)
+        plain = ws.GaussianRenderer.new(ctx, fmt, cloud["sh_deg"], cloud["compressed"])
+        plain.set_pair_capacity(min(max(8 * N, 1 << 22), (1 << 30) - 1))
+        plain.set_timing(False)
+        plain.prepare(None, fpc, cview)
+        plain.render_to_host(chk, fpc)
+        torch.cuda.synchronize()
+        checksum_n1 = bench.frame_crc(chk)
+        del plain, fpc, fgen, full
+    sync_all()
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -166,7 +200,9 @@ def run(args):
                          "peak": peak * world, "unit": "GB/s", "frac": (bytes_sort_blend / (sb_ms * 1e-3) / 1e9) / (peak * world) if sb_ms > 0 else 0.0,
                          "traffic": None, "peak_source": peak_src + " x n_gpus"},
             "cpu_baseline": None,
-            "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 448 * world, "d2h_bytes_per_step": W * H * 8},
+            "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 448 * world, "d2h_bytes_per_step": W * H * 8,
+                    "checksum": checksum, "checksum_what": "CRC-32 of the full RGBA16F frame of view %d, assembled from the %d ranks' bands and downloaded on rank 0" % (bench.CHECKSUM_VIEW, world),
+                    "checksum_n1_same_view": checksum_n1, "checksum_matches_n1": checksum == checksum_n1},
             "gpu_launches": K * world * (17 + (2 if depth > 1 else 0)),     # per rank and frame: 3 stage-1 + 3 routing (+2 gates) + 1 finish/histogram + 6 onesweep + 3 binning + 1 composite
             "clocks": clocks,
         }

@@ -94,6 +94,9 @@ typedef struct {
  * replaces PointCloud::new (src/pointcloud.rs:99-199).  Copies the host buffers to
  * HBM (synchronous); the caller keeps ownership of its memory. */
 WS_API ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_desc *desc, ws_pointcloud **out);
+/* Compressed clouds (here and in ws_pointcloud_create_from_c3dgs): every record's geometry_idx / sh_idx is checked
+ * once on the device against num_covars / the number of SH entries; an out-of-range index (wgpu would read zeros
+ * through its bounds-checked storage buffers, a CUDA gather would fault) fails with WS_ERR_INVALID_ARGUMENT. */
 /* .ply ingest: replaces PlyReader::new + read (src/io/ply.rs:28-48,165-195) and
  * GenericGaussianPointCloud::new (src/io/mod.rs:63-105).  `file_bytes` is the whole .ply file
  * (header + binary vertex block, little or big endian).  The header is parsed on the host; the
@@ -207,6 +210,13 @@ typedef struct {
  * (sort; here: depth sort, tile binning, tile sort, tile ranges). Asynchronous. */
 WS_API ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
                                      void *cuda_stream);
+/* Frame status without synchronising: everything above is asynchronous, so a frame that turns out incomplete on the
+ * device (pair capacity exceeded; internal error flags) cannot fail the call that enqueued it.  render() therefore
+ * copies the frame's status words into pinned host memory behind the frame, and the NEXT prepare() (or sharded
+ * frame call) that finds such a copy completed returns that earlier frame's error ONCE -- WS_ERR_PAIR_OVERFLOW or
+ * WS_ERR_CUDA, with ws_last_error() saying "an earlier frame was incomplete" -- without enqueueing anything; calling
+ * it again proceeds normally.  ws_renderer_stats() reports (and thereby consumes) the status of the frame it
+ * synchronises.  A caller that needs the status of frame k before using its pixels calls ws_renderer_stats(). */
 
 /* replaces GaussianRenderer::render (src/renderer.rs:250-260) together with the
  * caller's render pass (LoadOp::Clear(clear) on a target of color_format(),

@@ -85,6 +85,42 @@ def main():
             new = pipe.rebalance()                       # second round runs on the re-cut bands
             assert new == pipe.slots[1].bands
         dist.barrier()
+    # cfg5-style cloud (BASELINE.json configs[4]): every rank GENERATES only its own shard (seeded by rank, splat size of the
+    # whole cloud); the union is the cloud.  Rank 0 rebuilds the union, renders it on one GPU and compares bit for bit.
+    n_all, W, H = 800000, 1920, 1080
+    lo_i, hi_i = (n_all * rank) // world, (n_all * (rank + 1)) // world
+    mine = ws.synth.make_cloud(hi_i - lo_i, 4242 + 7919 * rank, density_n=n_all)
+    lo = torch.tensor(mine["aabb_min"], device="cuda"); hi = torch.tensor(mine["aabb_max"], device="cuda")
+    csum = torch.tensor(mine["center"].astype(np.float64) * (hi_i - lo_i), device="cuda")
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(csum)
+    meta = dict(aabb_min=lo.cpu().numpy(), aabb_max=hi.cpu().numpy(), center=(csum / n_all).cpu().numpy().astype(np.float32))
+    mine = dict(mine, **meta)
+    whole_meta = dict(mine, num_points=n_all)
+    pc = ws.PointCloud.new(ctx, make_generic(ws, mine))
+    pipe = ws.ShardedPipeline(ws, ctx, ws.FORMAT_RGBA16_FLOAT, 3, False, pc, n_all, (W, H), depth=2)
+    fovx, fovy = ws.synth.fov_for_viewport(W, H)
+    vargs = [make_args(ws, whole_meta, *ws.synth.orbit_camera(az), W, H, fovx, fovy) for az in (0.0, 120.0, 240.0)]
+    hosts = [torch.zeros((H, W, 4), dtype=torch.float16).pin_memory() for _ in vargs] if rank == 0 else [None] * len(vargs)
+    for a_, h_ in zip(vargs, hosts):
+        pipe.frame_peer(a_, root=0, host=h_)
+    pipe.synchronize()
+    torch.cuda.synchronize()
+    if rank == 0:
+        parts = [mine if q == 0 else ws.synth.make_cloud((n_all * (q + 1)) // world - (n_all * q) // world, 4242 + 7919 * q, density_n=n_all)
+                 for q in range(world)]
+        whole = dict(whole_meta, gaussians=np.concatenate([p_["gaussians"] for p_ in parts]),
+                     sh_coefs=np.concatenate([p_["sh_coefs"] for p_ in parts]))
+        full = ws.PointCloud.new(ctx, make_generic(ws, whole))
+        plain = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA16_FLOAT, 3, False)
+        for a_, h_ in zip(vargs, hosts):
+            plain.prepare(None, full, a_)
+            ref = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
+            plain.render(ref, full)
+            torch.cuda.synchronize()
+            same5 = torch.equal(h_, ref.cpu())
+            ok = ok and same5
+            print("cfg5-style: %d ranks x own shard (n=%d) identical=%s" % (world, n_all, same5), flush=True)
+    dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag.item()) == 1:

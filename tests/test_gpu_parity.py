@@ -445,3 +445,54 @@ def test_target_formats_against_rop_faithful_oracle(ws, orc, ctx):
     rop16 = orc.composite_rop(ref["splats"], ref["order"], W, H, 1)
     rel = np.abs(img16.astype(np.float32) - rop16).max(axis=2) / np.maximum(np.abs(rop16).max(axis=2), 2.0 ** -10)
     assert rel.max() < 6e-3 + 2e-3 and rel.mean() < 1e-3, (rel.max(), rel.mean())
+
+
+def test_deferred_frame_status_and_index_validation(ws, ctx):
+    """(1) A frame that overflowed the pair capacity cannot fail the asynchronous call that enqueued it; the NEXT
+    prepare() whose predecessor's status copy has landed returns WS_ERR_PAIR_OVERFLOW once, without synchronising.
+    (2) compressed records with out-of-range codebook indices are rejected at load time (a CUDA gather would fault
+    where wgpu's bounds-checked buffers read zeros).  (3) two contexts in one process (per-device kernel attributes)."""
+    import torch
+    cloud = ws.synth.make_cloud(3000, 4)
+    pc = ws.PointCloud.new(ctx, make_generic(ws, cloud))
+    r = ws.GaussianRenderer.new(ctx, ws.FORMAT_RGBA32_FLOAT, 3, False)
+    pos, rot = ws.synth.fixed_camera()
+    args = make_args(ws, cloud, pos, rot, 64, 48, *ws.synth.fov_for_viewport(64, 48))
+    t = torch.empty((48, 64, 4), device="cuda")
+    r.set_pair_capacity(100)
+    r.prepare(None, pc, args); r.render(t, pc)               # enqueued fine: the overflow happens on the device
+    torch.cuda.synchronize()
+    with pytest.raises(ws.WsError) as e:
+        r.prepare(None, pc, args)                            # reports the EARLIER frame, enqueues nothing
+    assert e.value.status == ws.WS_ERR_PAIR_OVERFLOW
+    r.set_pair_capacity(0)
+    r.prepare(None, pc, args); r.render(t, pc)               # reported once: the renderer keeps working
+    torch.cuda.synchronize()
+    r.prepare(None, pc, args); r.render(t, pc)
+    assert r.stats()["num_pairs"] > 100
+    # (2)
+    cc = ws.synth.make_cloud_compressed(2000, 9, codebook=64)
+    bad = dict(cc); bad["gaussians"] = cc["gaussians"].copy()
+    bad["gaussians"]["sh_idx"][17] = 64                      # one past the SH codebook
+    with pytest.raises(ws.WsError) as e:
+        ws.PointCloud.new(ctx, make_generic(ws, bad))
+    assert e.value.status == ws.WS_ERR_INVALID_ARGUMENT
+    bad["gaussians"] = cc["gaussians"].copy()
+    bad["gaussians"]["geometry_idx"][5] = 0xfffffff0         # a negative i32 in the file
+    with pytest.raises(ws.WsError):
+        ws.PointCloud.new(ctx, make_generic(ws, bad))
+    ws.PointCloud.new(ctx, make_generic(ws, cc))             # the untouched cloud loads
+    # (3) a second context on the same device (and on device 1 when there is one) renders the same frame
+    img0 = _frame(ws, ctx, cloud, pos, rot, 320, 200)[2]
+    for dev in range(min(torch.cuda.device_count(), 2)):
+        ctx2 = ws.Context(dev)
+        with torch.cuda.device(dev):
+            pc2 = ws.PointCloud.new(ctx2, make_generic(ws, cloud))
+            r2 = ws.GaussianRenderer.new(ctx2, ws.FORMAT_RGBA32_FLOAT, 3, False)
+            r2.set_occlusion_split(False)
+            a2 = make_args(ws, cloud, pos, rot, 320, 200, *ws.synth.fov_for_viewport(320, 200))
+            r2.prepare(None, pc2, a2)
+            t2 = torch.empty((200, 320, 4), dtype=torch.float32, device="cuda:%d" % dev)
+            r2.render(t2, pc2)
+            torch.cuda.synchronize(dev)
+            assert np.array_equal(t2.cpu().numpy(), img0)

@@ -65,11 +65,21 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpus_bit_identical_to_one():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_frames_bit_identical_to_one_gpu(world):
+    """G in {1, 2, 4, 8} images bit-identical.  tests/sharded_worker.py renders the same frames on `world`
+    GPUs (all three exchange variants, two frames in flight over re-cut bands, a cfg5-style cloud whose shards are
+    generated per rank) and on one GPU and requires torch.equal.  Needs `world` GPUs: `gpurun --gpus N`; the log of the
+    8-GPU run is committed under profiles/."""
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
     env = dict(os.environ, PYTHONPATH=ROOT)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "sharded_worker.py")]
-    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(29517 + world), os.path.join(ROOT, "tests", "sharded_worker.py")]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    log = os.environ.get("WS_SHARDED_LOG_DIR")
+    if log:
+        with open(os.path.join(log, "sharded_worker_world%d.log" % world), "w") as f:
+            f.write(p.stdout[-20000:] + "\n--- stderr tail ---\n" + p.stderr[-3000:])
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "SHARDED_OK" in p.stdout

@@ -67,13 +67,15 @@ inline Array parse_npy(const std::vector<uint8_t> &raw, const std::string &name)
     size_t hlen, hoff;
     if (major == 1) { hlen = rd16(raw.data() + 8); hoff = 10; }
     else { if (raw.size() < 12) throw std::runtime_error("npz: truncated .npy header"); hlen = rd32(raw.data() + 8); hoff = 12; }
-    if (hoff + hlen > raw.size()) throw std::runtime_error("npz: truncated .npy header in '" + name + "'");
+    if (hlen > raw.size() - hoff) throw std::runtime_error("npz: truncated .npy header in '" + name + "'");
     const std::string h(reinterpret_cast<const char *>(raw.data() + hoff), hlen);
     Array a;
     auto value_after = [&](const char *key) -> size_t {
         const size_t k = h.find(key);
         if (k == std::string::npos) throw std::runtime_error("npz: .npy header of '" + name + "' lacks " + key);
-        return h.find(':', k) + 1;
+        const size_t c = h.find(':', k);
+        if (c == std::string::npos) throw std::runtime_error("npz: malformed .npy header in '" + name + "'");
+        return c + 1;
     };
     {
         size_t p = h.find('\'', value_after("'descr'"));
@@ -81,7 +83,10 @@ inline Array parse_npy(const std::vector<uint8_t> &raw, const std::string &name)
         if (p == std::string::npos || e == std::string::npos) throw std::runtime_error("npz: structured dtypes are not supported ('" + name + "')");
         a.descr = h.substr(p + 1, e - p - 1);
     }
-    a.fortran_order = h.compare(h.find_first_not_of(' ', value_after("'fortran_order'")), 4, "True") == 0;
+    {
+        const size_t f = h.find_first_not_of(' ', value_after("'fortran_order'"));
+        a.fortran_order = f != std::string::npos && h.compare(f, 4, "True") == 0;
+    }
     {
         const size_t p = h.find('(', value_after("'shape'")), e = h.find(')', p);
         if (p == std::string::npos || e == std::string::npos) throw std::runtime_error("npz: bad shape in '" + name + "'");
@@ -96,8 +101,17 @@ inline Array parse_npy(const std::vector<uint8_t> &raw, const std::string &name)
         }
     }
     if (a.descr.size() < 3 || (a.descr[0] == '>' && a.itemsize() > 1)) throw std::runtime_error("npz: big-endian / unsupported dtype '" + a.descr + "' in '" + name + "'");
-    const size_t need = a.count() * a.itemsize();
-    if (hoff + hlen + need > raw.size()) throw std::runtime_error("npz: member '" + name + "' is shorter than its shape says");
+    // overflow-safe element count: a shape like (2^63, 2) must not wrap to a small byte count
+    const size_t avail = raw.size() - hoff - hlen, isz = a.itemsize();
+    if (isz == 0) throw std::runtime_error("npz: unsupported dtype '" + a.descr + "' in '" + name + "'");
+    size_t cnt = 1;
+    for (size_t d : a.shape) if (d == 0) cnt = 0;                    // an empty array holds no data whatever the other extents
+    if (cnt) for (size_t d : a.shape) {
+        if (cnt > avail / d) throw std::runtime_error("npz: member '" + name + "' is shorter than its shape says");
+        cnt *= d;
+    }
+    if (cnt > avail / isz) throw std::runtime_error("npz: member '" + name + "' is shorter than its shape says");
+    const size_t need = cnt * isz;
     a.data.assign(raw.begin() + hoff + hlen, raw.begin() + hoff + hlen + need);
     return a;
 }
@@ -146,30 +160,40 @@ inline std::map<std::string, Array> read(const uint8_t *bytes, size_t len)
     if (entries == 0xffffu || cd_off == 0xffffffffu) {               // zip64: locator 20 B in front of the EOCD
         if (eocd < 20 || rd32(bytes + eocd - 20) != 0x07064b50u) throw std::runtime_error("npz: zip64 locator missing");
         const uint64_t e64 = rd64(bytes + eocd - 20 + 8);
-        if (e64 + 56 > len || rd32(bytes + e64) != 0x06064b50u) throw std::runtime_error("npz: bad zip64 end-of-central-directory record");
+        if (e64 > len || len - e64 < 56 || rd32(bytes + e64) != 0x06064b50u) throw std::runtime_error("npz: bad zip64 end-of-central-directory record");
         entries = rd64(bytes + e64 + 32); cd_off = rd64(bytes + e64 + 48);
     }
+    // every offset / size below comes from the file: compare against what is LEFT (len - x), never x + size > len (wraps)
+    if (cd_off > len) throw std::runtime_error("npz: central directory offset beyond the file");
+    if (entries > (len - cd_off) / 46) throw std::runtime_error("npz: more central directory entries than the file can hold");
     std::map<std::string, Array> out;
     uint64_t p = cd_off;
     for (uint64_t i = 0; i < entries; i++) {
-        if (p + 46 > len || rd32(bytes + p) != 0x02014b50u) throw std::runtime_error("npz: bad central directory entry");
+        if (p > len || len - p < 46 || rd32(bytes + p) != 0x02014b50u) throw std::runtime_error("npz: bad central directory entry");
         const uint16_t method = rd16(bytes + p + 10), nlen = rd16(bytes + p + 28), xlen = rd16(bytes + p + 30), clen = rd16(bytes + p + 32);
         uint64_t csize = rd32(bytes + p + 20), usize = rd32(bytes + p + 24), lho = rd32(bytes + p + 42);
+        if (len - p - 46 < (uint64_t)nlen + xlen + clen) throw std::runtime_error("npz: central directory entry runs past the end of the file");
         std::string name(reinterpret_cast<const char *>(bytes + p + 46), nlen);
-        // zip64 extended information (header id 1): the 0xffffffff fields, in this order
+        // zip64 extended information (header id 1): the 0xffffffff fields, in this order, each inside the sub-field's size
         for (uint64_t x = p + 46 + nlen, xe = x + xlen; x + 4 <= xe; ) {
             const uint16_t id = rd16(bytes + x), sz = rd16(bytes + x + 2);
+            if (x + 4 + sz > xe) throw std::runtime_error("npz: extra field of '" + name + "' runs past its record");
             if (id == 1) {
                 uint64_t q = x + 4;
-                if (usize == 0xffffffffu) { usize = rd64(bytes + q); q += 8; }
-                if (csize == 0xffffffffu) { csize = rd64(bytes + q); q += 8; }
-                if (lho == 0xffffffffu) { lho = rd64(bytes + q); q += 8; }
+                const uint64_t qe = q + sz;
+                auto take64 = [&](uint64_t &v) { if (qe - q < 8) throw std::runtime_error("npz: short zip64 extra field in '" + name + "'"); v = rd64(bytes + q); q += 8; };
+                if (usize == 0xffffffffu) take64(usize);
+                if (csize == 0xffffffffu) take64(csize);
+                if (lho == 0xffffffffu) take64(lho);
             }
             x += 4 + sz;
         }
-        if (lho + 30 > len || rd32(bytes + lho) != 0x04034b50u) throw std::runtime_error("npz: bad local header for '" + name + "'");
+        if (lho > len || len - lho < 30 || rd32(bytes + lho) != 0x04034b50u) throw std::runtime_error("npz: bad local header for '" + name + "'");
         const uint64_t data = lho + 30 + rd16(bytes + lho + 26) + rd16(bytes + lho + 28);
-        if (data + csize > len) throw std::runtime_error("npz: member '" + name + "' is truncated");
+        if (data > len || csize > len - data) throw std::runtime_error("npz: member '" + name + "' is truncated");
+        // a stored member is as long as its data; a deflated one cannot expand beyond deflate's ~1032:1 bound
+        if ((method == 0 && usize != csize) || (method == 8 && usize / 1040 > csize + 1))
+            throw std::runtime_error("npz: implausible uncompressed size for '" + name + "'");
         std::vector<uint8_t> raw;
         if (method == 0) raw.assign(bytes + data, bytes + data + csize);
         else if (method == 8) raw = inflate_raw(bytes + data, csize, usize, name);

@@ -133,11 +133,11 @@ bin_scan_kernel(BinningArgs a)
     uint32_t lo, hi;
     slab_bounds(a, V, lo, hi);
     const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
-    const uint32_t total_out = block_exclusive_scan_1024(a.part_counts, a.part_bases, nparts);
+    const uint64_t total_out = block_exclusive_scan_1024(a.part_counts, a.part_bases, nparts);
     if (threadIdx.x == 0) {
-        const uint32_t P = (nparts > 0u) ? total_out : 0u;
-        *a.num_pairs_out = P;
-        if (P > a.pair_cap) a.counters->pair_overflow = 1u;            // zeroed per frame; either slab may set it
+        const uint64_t P = (nparts > 0u) ? total_out : 0ull;           // 64-bit: screen-filling splats can push P past 2^32
+        *a.num_pairs_out = P > 0xffffffffull ? 0xffffffffu : (uint32_t)P;
+        if (P > (uint64_t)a.pair_cap) a.counters->pair_overflow = 1u;  // zeroed per frame; either slab may set it
     }
 }
 
@@ -169,6 +169,7 @@ bin_expand_kernel(BinningArgs a)
         SplatRects r;
         load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r, a.tile_done ? a.keep4[part * BIN_THREADS + tid] : 0x01010101u);
         const uint32_t base = __ldg(a.part_bases + part);
+        if (base >= cap) continue;                        // beyond the pair capacity (overflow is already flagged): nothing of this partition is stored
         const uint32_t mine = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
         // block scan of the per-thread totals
         uint32_t incl = mine;

@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -174,6 +175,12 @@ static void build_camera_uniform(const ws_splatting_args *a, CameraUniform *u)
 }
 
 // ------------------------------------------------------------------------------------
+static uint64_t next_generation()
+{
+    static std::atomic<uint64_t> g{1};
+    return g.fetch_add(1, std::memory_order_relaxed);
+}
+
 struct ws_pointcloud {
     ws_context *ctx;
     uint32_t n, sh_deg;
@@ -189,6 +196,7 @@ struct ws_pointcloud {
     int32_t has_bg; float bg[3];
     size_t sh_bytes = 0;           // bytes of SH payload in d_sh (read-back)
     uint32_t num_covars = 0;
+    uint64_t generation = next_generation();   // identity of THIS cloud in CUDA-graph cache keys (a freed cloud's address may be reused)
 };
 
 extern "C" void ws_pointcloud_destroy(ws_pointcloud *pc)
@@ -197,6 +205,21 @@ extern "C" void ws_pointcloud_destroy(ws_pointcloud *pc)
     cudaSetDevice(pc->ctx->device);
     cudaFree(pc->d_gaussians); cudaFree(pc->d_sh); cudaFree(pc->d_covars); cudaFree(pc->d_xyz);
     delete pc;
+}
+
+// load-time check of the two index fields of compressed records (ingest.cu: validate_compressed_kernel)
+static ws_status validate_compressed_indices(ws_context *ctx, const uint8_t *d_gaussians, uint32_t n, uint32_t num_covars, uint32_t num_features)
+{
+    if (!n) return WS_OK;
+    uint32_t *d_flag = nullptr, h_flag = 0;
+    CU(cudaMalloc(&d_flag, 4));
+    cudaError_t e = cudaMemset(d_flag, 0, 4);
+    if (e == cudaSuccess) e = launch_validate_compressed(d_gaussians, n, num_covars, num_features, d_flag, ctx->sm_count * 8, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) return fail_cuda(e, "validate_compressed_indices");
+    if (h_flag) return fail(WS_ERR_INVALID_ARGUMENT, "compressed cloud: geometry_idx / sh_idx out of range of the codebooks");
+    return WS_OK;
 }
 
 extern "C" ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_desc *d, ws_pointcloud **out)
@@ -246,6 +269,12 @@ extern "C" ws_status ws_pointcloud_create(ws_context *ctx, const ws_pointcloud_d
         if (cb) PC_CU(cudaMemcpy(pc->d_covars, d->covars, cb, cudaMemcpyHostToDevice));
     }
 #undef PC_CU
+    if (d->compressed) {
+        const uint32_t per = (d->sh_deg + 1u) * (d->sh_deg + 1u) * 3u;
+        const uint64_t nf = d->sh_bytes / per;
+        ws_status vs = validate_compressed_indices(ctx, pc->d_gaussians, n, (uint32_t)d->num_covars, nf > 0xffffffffull ? 0xffffffffu : (uint32_t)nf);
+        if (vs != WS_OK) { ws_pointcloud_destroy(pc); return vs; }
+    }
     *out = pc;
     return WS_OK;
 }
@@ -567,6 +596,10 @@ extern "C" ws_status ws_pointcloud_create_from_c3dgs(ws_context *ctx, const ws_c
     NPZ_CU(cudaMemcpy(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost));
 #undef NPZ_CU
     cudaFree(d_in); cudaFree(d_sums);
+    {   // gaussian_indices / feature_indices come from the file: reject out-of-range (incl. negative) entries
+        ws_status vs = validate_compressed_indices(ctx, pc->d_gaussians, n, nc, nf);
+        if (vs != WS_OK) { ws_pointcloud_destroy(pc); return vs; }
+    }
     pc->sh_bytes = shb; pc->num_covars = nc;
     finish_cloud_stats(pc, n, sums, mm, 1.f);
     *out = pc;
@@ -716,7 +749,16 @@ struct ws_renderer {
     int tile_out_far = 0;
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t prep_exec = nullptr;
-    struct { const ws_pointcloud *pc; const void *gaussians, *scratch, *state; uint32_t n, W, H, pair_cap, n_cap; bool split; } prep_key = {};
+    // deferred frame status: render() copies {V, P, pair_overflow, error_flags} of its frame into a ring of pinned slots;
+    // the NEXT prepare()/render() whose predecessor's copy has completed returns that frame's error once
+    // (WS_ERR_PAIR_OVERFLOW / WS_ERR_CUDA) instead of WS_OK -- no synchronisation; ws_renderer_stats() consumes them too
+    static constexpr int FLAG_SLOTS = 4;
+    uint32_t *h_flags = nullptr;           // pinned, FLAG_SLOTS x 4 words
+    cudaEvent_t ev_flags[FLAG_SLOTS] = {};
+    bool flags_pending[FLAG_SLOTS] = {};
+    int flag_next = 0;
+    uint64_t buf_generation = 0;           // bumped whenever a buffer a captured graph points into is (re)allocated
+    struct { const ws_pointcloud *pc; uint64_t pc_gen, buf_gen; const void *gaussians, *scratch, *state; uint32_t n, W, H, pair_cap, n_cap; bool split; } prep_key = {};
 };
 
 static void free_shard(ws_renderer *r);
@@ -743,6 +785,8 @@ extern "C" void ws_renderer_destroy(ws_renderer *r)
     free_sort_stuff(r);
     cudaFree(r->d_uniforms); cudaFree(r->d_ranges); cudaFree(r->d_frame); cudaFree(r->d_state); cudaFree(r->d_tile_done);
     if (r->ev_ok) for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(r->ev[i]);
+    for (int i = 0; i < ws_renderer::FLAG_SLOTS; i++) if (r->ev_flags[i]) cudaEventDestroy(r->ev_flags[i]);
+    if (r->h_flags) cudaFreeHost(r->h_flags);
     if (r->prep_exec) cudaGraphExecDestroy(r->prep_exec);
     if (r->cap_stream) cudaStreamDestroy(r->cap_stream);
     delete r;
@@ -765,6 +809,9 @@ extern "C" ws_status ws_renderer_create(ws_context *ctx, ws_format fmt, uint32_t
         if (e != cudaSuccess) { ws_status s = fail_cuda(e, "cudaEventCreate"); ws_renderer_destroy(r); return s; }
     }
     r->ev_ok = true;
+    e = cudaHostAlloc(reinterpret_cast<void **>(&r->h_flags), ws_renderer::FLAG_SLOTS * 16, cudaHostAllocDefault);
+    for (int i = 0; i < ws_renderer::FLAG_SLOTS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&r->ev_flags[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { ws_status s = fail_cuda(e, "deferred-status slots"); ws_renderer_destroy(r); return s; }
     // persistent grids: one wave of resident CTAs
     r->grid_pre = ctx->sm_count * preprocess_blocks_per_sm(r->compressed);
     r->grid_sort = ctx->sm_count * sort_pass_blocks_per_sm();
@@ -862,6 +909,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         CU(cudaMalloc(&r->d_rects, nn * 8));
         CU(cudaMalloc(&r->d_keep4, (nn / 2 + 2 * 1024 + 4) / 4 * 4 + 4096));   // far slab rounded up to whole 1024-splat partitions
         r->n_cap = n; r->pair_cap = pair_cap;
+        r->buf_generation = next_generation();
     }
     if (!r->d_ranges || r->tiles_cap < tiles) {
         cudaFree(r->d_ranges); r->d_ranges = nullptr;
@@ -869,6 +917,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         cudaFree(r->d_tile_done); r->d_tile_done = nullptr;
         CU(cudaMalloc(&r->d_tile_done, tiles ? tiles : 1));
         r->tiles_cap = tiles;
+        r->buf_generation = next_generation();
     }
     return WS_OK;
 }
@@ -889,6 +938,23 @@ static void build_settings_uniform(const ws_splatting_args *a, const ws_pointclo
     float ext = a->has_scene_extend ? a->scene_extend : rad;
     if (!(ext > rad)) ext = rad;                                       // .max(pc.bbox().radius())
     s->scene_extend = ext;
+}
+
+// Error of an EARLIER frame whose status copy has completed (see ws_renderer::h_flags); reported once.
+static ws_status take_deferred_status(ws_renderer *r)
+{
+    ws_status st = WS_OK;
+    for (int i = 0; i < ws_renderer::FLAG_SLOTS; i++) {
+        if (!r->flags_pending[i] || cudaEventQuery(r->ev_flags[i]) != cudaSuccess) continue;
+        r->flags_pending[i] = false;
+        const uint32_t *f = r->h_flags + 4 * i;
+        if (st == WS_OK && f[3]) st = WS_ERR_CUDA;
+        if (st == WS_OK && f[2]) st = WS_ERR_PAIR_OVERFLOW;
+    }
+    cudaGetLastError();                                 // cudaErrorNotReady of a query is not an error
+    if (st == WS_ERR_CUDA) return fail(st, "an earlier frame was incomplete: internal error flags set (look-back watchdog / receive capacity / peer wait)");
+    if (st == WS_ERR_PAIR_OVERFLOW) return fail(st, "an earlier frame was incomplete: pair capacity exceeded; raise it with ws_renderer_set_pair_capacity");
+    return WS_OK;
 }
 
 static ws_status validate_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args)
@@ -1042,6 +1108,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     if (r->shard.world > 1) return fail(WS_ERR_INVALID_ARGUMENT, "renderer is configured for sharding: use ws_renderer_shard_begin/exchange/finish");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
+    st = take_deferred_status(r);
+    if (st != WS_OK) return st;
     // auto: the six extra launches and the state round trip pay off only when there are many pairs to save -- measured
     // cfg 1 (100 K points) -14 %, cfg 2 (1 M) -2 %, cfg 3 (6 M) +7 %
     r->frame_split = r->shard.world == 0 && (r->split_mode == 1 || (r->split_mode == 2 && pc->n >= 2000000u));
@@ -1051,6 +1119,7 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
             cudaFree(r->d_state); r->d_state = nullptr; r->state_px = 0;
             CU(cudaMalloc(&r->d_state, px * sizeof(float4)));
             r->state_px = px;
+            r->buf_generation = next_generation();
         }
     }
     st = begin_frame(r, pc, args, pc->n, stream, /*with_clears=*/false);     // uniforms only; capacities may (re)allocate
@@ -1060,7 +1129,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
         // reads its sizes (N, V, P) from device memory, so the graph is independent of the frame's content.
         const FrameUniforms &U = r->h_uniforms;
         auto &k = r->prep_key;
-        const bool same = r->prep_exec && k.pc == pc && k.gaussians == pc->d_gaussians && k.scratch == r->d_scratch && k.n == pc->n &&
+        const bool same = r->prep_exec && k.pc == pc && k.pc_gen == pc->generation && k.buf_gen == r->buf_generation &&
+                          k.gaussians == pc->d_gaussians && k.scratch == r->d_scratch && k.n == pc->n &&
                           k.W == U.width && k.H == U.height && k.pair_cap == r->pair_cap && k.n_cap == r->n_cap &&
                           k.split == r->frame_split && k.state == (const void *)r->d_state;
         if (!same) {
@@ -1075,7 +1145,7 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
             e = cudaGraphInstantiate(&r->prep_exec, g, 0);
             cudaGraphDestroy(g);
             if (e != cudaSuccess) { r->prep_exec = nullptr; return fail_cuda(e, "cudaGraphInstantiate"); }
-            k.pc = pc; k.gaussians = pc->d_gaussians; k.scratch = r->d_scratch; k.n = pc->n; k.W = U.width; k.H = U.height;
+            k.pc = pc; k.pc_gen = pc->generation; k.buf_gen = r->buf_generation; k.gaussians = pc->d_gaussians; k.scratch = r->d_scratch; k.n = pc->n; k.W = U.width; k.H = U.height;
             k.pair_cap = r->pair_cap; k.n_cap = r->n_cap; k.split = r->frame_split; k.state = r->d_state;
         }
         CU(cudaGraphLaunch(r->prep_exec, stream));
@@ -1315,6 +1385,8 @@ extern "C" ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointclo
     if (pc->n > s.local_cap) return fail(WS_ERR_INVALID_ARGUMENT, "local shard larger than configured");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
+    st = take_deferred_status(r);
+    if (st != WS_OK) return st;
     r->frame_split = false;
     st = begin_frame(r, pc, args, s.recv_cap, stream);
     if (st != WS_OK) return st;
@@ -1442,6 +1514,12 @@ static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_
     if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND0], stream));
     if (tile_rows) CU(launch_composite(a, U.tiles_x, tile_rows, stream));
     if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND1], stream));
+    {   // this frame's {V, P, pair_overflow, error_flags} -> a pinned slot; checked (never waited for) by later calls
+        const int slot = r->flag_next; r->flag_next = (slot + 1) % ws_renderer::FLAG_SLOTS;
+        CU(cudaMemcpyAsync(r->h_flags + 4 * slot, r->d_counters, 16, cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(r->ev_flags[slot], stream));
+        r->flags_pending[slot] = true;
+    }
     r->rendered = true;
     r->last_stream = stream;
     return WS_OK;
@@ -1498,6 +1576,7 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
     FrameCounters c;
     ws_status st = read_counters(r, &c);
     if (st != WS_OK) return st;
+    for (int i = 0; i < ws_renderer::FLAG_SLOTS; i++) r->flags_pending[i] = false;   // this call reports the frame's status itself
     const FrameUniforms &U = r->h_uniforms;
     s->num_points = r->last_n; s->num_visible = c.num_visible;
     s->num_pairs = (uint64_t)c.num_pairs + (r->frame_split ? c.num_pairs_near : 0u);      // split frames: near slab + what the far slab still had to emit
@@ -1531,7 +1610,7 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
         s->bytes_sort += (V / 2) * 12;
         s->bytes_blend += T * 8 + (uint64_t)U.width * U.height * 32;
     }
-    if (c.error_flags) return fail(WS_ERR_CUDA, "internal: decoupled look-back watchdog fired");
+    if (c.error_flags) return fail(WS_ERR_CUDA, (c.error_flags & 2u) ? "sharded frame: receive capacity exceeded" : ((c.error_flags & 4u) ? "sharded frame: a peer never arrived" : "internal: decoupled look-back watchdog fired"));
     if (c.pair_overflow) return fail(WS_ERR_PAIR_OVERFLOW, "pair capacity exceeded; raise it with ws_renderer_set_pair_capacity");
     return WS_OK;
 }

@@ -199,7 +199,30 @@ c3dgs_covars_kernel(C3dgsArgs a)
     }
 }
 
+// Index validation of compressed (24-B) records: geometry_idx / sh_idx come from an untrusted file or caller.  wgpu's
+// storage buffers are bounds-checked (an out-of-range index reads zeros); a CUDA gather is not -- one bad index would
+// fault the context -- so clouds are checked ONCE at load time and rejected with WS_ERR_INVALID_ARGUMENT.
+__global__ void __launch_bounds__(256)
+validate_compressed_kernel(const uint8_t *__restrict__ gaussians, uint32_t n, uint32_t num_covars, uint32_t num_features, uint32_t *flag)
+{
+    bool bad = false;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        const uint32_t *rec = reinterpret_cast<const uint32_t *>(gaussians + (size_t)i * 24u);
+        bad = bad || (rec[4] >= num_covars) || (rec[5] >= num_features);
+    }
+    if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(flag, 1u);
+}
+
 }  // namespace
+
+cudaError_t launch_validate_compressed(const uint8_t *gaussians, uint32_t n, uint32_t num_covars, uint32_t num_features,
+                                       uint32_t *flag, int max_grid, cudaStream_t stream)
+{
+    if (!n) return cudaSuccess;
+    const uint64_t w = ((uint64_t)n + 255u) / 256u;
+    validate_compressed_kernel<<<(unsigned)(w < (uint64_t)max_grid ? w : (uint64_t)max_grid), 256, 0, stream>>>(gaussians, n, num_covars, num_features, flag);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ply_convert(const PlyConvertArgs &a, int grid, cudaStream_t stream)
 {

@@ -393,8 +393,8 @@ scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, c
 {
     const uint32_t n = uniforms->num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
-    const uint32_t total = block_exclusive_scan_1024(counts, bases, nparts);
-    if (threadIdx.x == 0) counters->num_visible = total;
+    const uint64_t total = block_exclusive_scan_1024(counts, bases, nparts);
+    if (threadIdx.x == 0) counters->num_visible = (uint32_t)total;     // <= N < 2^32
 }
 
 // ---- (3) MAIN ---------------------------------------------------------------------------------
@@ -567,13 +567,18 @@ preprocess_kernel(PreprocessArgs a)
 
 }  // namespace
 
+// The opt-in above 48 KB of dynamic shared memory is a per-device attribute: the C ABI allows several ws_context on
+// different devices in one process, so it is tracked per device (and per layout).
 template <bool C>
 static cudaError_t pp_prepare()
 {
-    static bool done = false;
-    if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PPSmem<C>::bytes);
-    if (e == cudaSuccess) done = true;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(preprocess_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PPSmem<C>::bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }
 

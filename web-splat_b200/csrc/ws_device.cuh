@@ -170,48 +170,69 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t *flag, uint32_t epoch,
     return true;
 }
 
-// Exclusive scan of counts[0..n) into bases[0..n) by ONE CTA of 1024 threads; returns the total to every thread.
-// 4096-element tiles, four adjacent elements per thread: every element is read once (coalesced enough for L1 to
-// merge), scanned in registers + shuffles, and written once; three barriers per tile.  (The first version gave each
-// thread one long contiguous chunk and read it twice: 18 us for 23 K counts, half of it LSU-queue throttling.)
-__device__ __forceinline__ uint32_t block_exclusive_scan_1024(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, uint32_t n)
+// Exclusive scan of counts[0..n) into bases[0..n) by ONE CTA of 1024 threads; returns the total (64-bit) to every thread.
+// 16 K-element tiles, sixteen adjacent elements per thread (four 128-bit loads in flight before the first use): every
+// element is read once, scanned in registers + shuffles, written once; three barriers per tile.  cfg3's 23.4 K partition
+// counts are two tiles (the round-1 version used 4 K tiles: six dependent trips, 14 us).  The running total is kept in
+// 64 bits: pair counts can exceed 2^32 (screen-filling splats); bases saturate at 0xffffffff, which every consumer
+// treats as "beyond capacity", so an overflow is reported instead of wrapping into a silently wrong frame.
+// counts / bases must be 16-byte aligned (they are 256-byte aligned slices of the scratch allocation).
+__device__ __forceinline__ uint64_t block_exclusive_scan_1024(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, uint32_t n)
 {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_tot, s_carry;
+    constexpr int E = 16;
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_tot, s_carry;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_carry = 0u;
+    if (tid == 0) s_carry = 0ull;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 4096u) {
-        const uint32_t i0 = base + tid * 4u;
-        uint32_t c[4];
+    for (uint32_t base = 0; base < n; base += 1024u * E) {
+        const uint32_t i0 = base + tid * E;
+        uint32_t c[E];
+        if (i0 + E <= n) {
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(counts + i0);
 #pragma unroll
-        for (int k = 0; k < 4; k++) c[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
-        const uint32_t sum = c[0] + c[1] + c[2] + c[3];
-        uint32_t incl = sum;
+            for (int q = 0; q < E / 4; q++) { const uint4 v = p4[q]; c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) c[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
+        }
+        uint64_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < E; k++) sum += c[k];
+        uint64_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)lane >= o) incl += t;
         }
         if (lane == 31) s_w[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const uint32_t v = s_w[lane];
-            uint32_t vi = v;
+            const uint64_t v = s_w[lane];
+            uint64_t vi = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+                const uint64_t t = __shfl_up_sync(0xffffffffu, vi, o);
                 if ((int)lane >= o) vi += t;
             }
             s_w[lane] = vi - v;                                   // exclusive offset of each warp
             if (lane == 31) s_tot = vi;
         }
         __syncthreads();
-        uint32_t run = s_carry + s_w[warp] + incl - sum;
+        uint64_t run = s_carry + s_w[warp] + incl - sum;
+        if (i0 + E <= n) {
+            uint32_t o[E];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (i0 + k < n) bases[i0 + k] = run;
-            run += c[k];
+            for (int k = 0; k < E; k++) { o[k] = run > 0xffffffffull ? 0xffffffffu : (uint32_t)run; run += c[k]; }
+            uint4 *p4 = reinterpret_cast<uint4 *>(bases + i0);
+#pragma unroll
+            for (int q = 0; q < E / 4; q++) p4[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                if (i0 + k < n) bases[i0 + k] = run > 0xffffffffull ? 0xffffffffu : (uint32_t)run;
+                run += c[k];
+            }
         }
         __syncthreads();                                           // everyone has read s_carry / s_w
         if (tid == 0) s_carry += s_tot;

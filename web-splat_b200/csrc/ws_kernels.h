@@ -127,6 +127,9 @@ struct C3dgsArgs {                // device copies of the .npz arrays (io/npz.rs
     double *sums; uint32_t *minmax;
 };
 cudaError_t launch_c3dgs_convert(const C3dgsArgs &a, int max_grid, cudaStream_t stream);
+// sets *flag != 0 when a 24-B record's geometry_idx >= num_covars or sh_idx >= num_features (flag zeroed by the caller)
+cudaError_t launch_validate_compressed(const uint8_t *gaussians, uint32_t n, uint32_t num_covars, uint32_t num_features,
+                                       uint32_t *flag, int max_grid, cudaStream_t stream);
 
 // ---- multi-GPU exchange (shard.cu) ---------------------------------------------------------------
 struct RouteArgs {
