@@ -17,10 +17,17 @@
  * analytic cases.
  *
  * Every function cites the reference file:line it follows (paths relative to
- * /root/reference).  Arithmetic is IEEE binary32 with one rounding per
- * operation, in the operation order written here (compile with
- * -ffp-contract=off); WGSL leaves operation order / contraction to the
- * implementation, so this file fixes ONE conforming evaluation order.
+ * /root/reference).  Arithmetic is IEEE binary32 in the operation order written
+ * here; the compiler may not contract (-ffp-contract=off), so a fused
+ * multiply-add happens exactly where fmaf() is written and nowhere else.  WGSL
+ * leaves operation order, contraction and the accuracy of `/` (2.5 ulp) to the
+ * implementation, so this file fixes ONE conforming evaluation: dot products
+ * and matrix products accumulate with fmaf(), and a quotient whose divisor is
+ * shared (x/w, y/w, z/w; J's 1/z; normalize) is formed as a correctly rounded
+ * reciprocal times the numerator.  The sm_100a kernels mirror it operation for
+ * operation (FFMA / MUFU.RCP + Newton = __frcp_rn), which is what keeps stage 1
+ * bit-exact between the two while costing ~20 % fewer instructions than the
+ * round-1 "one rounding per written operation" form.
  */
 #include <math.h>
 #include <stdint.h>
@@ -221,6 +228,10 @@ typedef struct { float v[3]; } vec3;
 static inline vec3 v3s(float s, vec3 a) { vec3 r = {{ s * a.v[0], s * a.v[1], s * a.v[2] }}; return r; }
 static inline vec3 v3add(vec3 a, vec3 b) { vec3 r = {{ a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2] }}; return r; }
 static inline vec3 v3sub(vec3 a, vec3 b) { vec3 r = {{ a.v[0] - b.v[0], a.v[1] - b.v[1], a.v[2] - b.v[2] }}; return r; }
+/* acc + s * a per channel, fused */
+static inline vec3 v3fma(float s, vec3 a, vec3 acc) { vec3 r = {{ fmaf(s, a.v[0], acc.v[0]), fmaf(s, a.v[1], acc.v[1]), fmaf(s, a.v[2], acc.v[2]) }}; return r; }
+/* correctly rounded reciprocal (IEEE division of 1 by x) */
+static inline float rcp(float x) { return 1.0f / x; }
 
 /* evaluate_sh, preprocess.wgsl:124-154 (identical in the compressed shader :174-204).
  * sh[k] = k-th RGB coefficient triple, already decoded to f32. */
@@ -230,25 +241,25 @@ static vec3 evaluate_sh(const float dir[3], const vec3 sh[16], uint32_t deg)
     if (deg > 0u) {
         float x = dir[0], y = dir[1], z = dir[2];
         vec3 t = v3s((-SH_C1) * y, sh[1]);
-        t = v3add(t, v3s(SH_C1 * z, sh[2]));
-        t = v3sub(t, v3s(SH_C1 * x, sh[3]));
+        t = v3fma(SH_C1 * z, sh[2], t);
+        t = v3fma(-(SH_C1 * x), sh[3], t);
         result = v3add(result, t);
         if (deg > 1u) {
             float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             vec3 u = v3s(SH_C2[0] * xy, sh[4]);
-            u = v3add(u, v3s(SH_C2[1] * yz, sh[5]));
-            u = v3add(u, v3s(SH_C2[2] * (2.0f * zz - xx - yy), sh[6]));
-            u = v3add(u, v3s(SH_C2[3] * xz, sh[7]));
-            u = v3add(u, v3s(SH_C2[4] * (xx - yy), sh[8]));
+            u = v3fma(SH_C2[1] * yz, sh[5], u);
+            u = v3fma(SH_C2[2] * (2.0f * zz - xx - yy), sh[6], u);
+            u = v3fma(SH_C2[3] * xz, sh[7], u);
+            u = v3fma(SH_C2[4] * (xx - yy), sh[8], u);
             result = v3add(result, u);
             if (deg > 2u) {
                 vec3 w = v3s(SH_C3[0] * y * (3.0f * xx - yy), sh[9]);
-                w = v3add(w, v3s(SH_C3[1] * xy * z, sh[10]));
-                w = v3add(w, v3s(SH_C3[2] * y * (4.0f * zz - xx - yy), sh[11]));
-                w = v3add(w, v3s(SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), sh[12]));
-                w = v3add(w, v3s(SH_C3[4] * x * (4.0f * zz - xx - yy), sh[13]));
-                w = v3add(w, v3s(SH_C3[5] * z * (xx - yy), sh[14]));
-                w = v3add(w, v3s(SH_C3[6] * x * (xx - 3.0f * yy), sh[15]));
+                w = v3fma(SH_C3[1] * xy * z, sh[10], w);
+                w = v3fma(SH_C3[2] * y * (4.0f * zz - xx - yy), sh[11], w);
+                w = v3fma(SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), sh[12], w);
+                w = v3fma(SH_C3[4] * x * (4.0f * zz - xx - yy), sh[13], w);
+                w = v3fma(SH_C3[5] * z * (xx - yy), sh[14], w);
+                w = v3fma(SH_C3[6] * x * (xx - 3.0f * yy), sh[15], w);
                 result = v3add(result, w);
             }
         }
@@ -257,14 +268,14 @@ static vec3 evaluate_sh(const float dir[3], const vec3 sh[16], uint32_t deg)
     return result;
 }
 
-/* mat4 (column-major) * vec4, summed left to right */
+/* mat4 (column-major) * vec4, accumulated left to right with fused multiply-adds */
 static inline void m4v4(const float *m, const float v[4], float out[4])
 {
     for (int r = 0; r < 4; r++) {
         float acc = m[0 * 4 + r] * v[0];
-        acc = acc + m[1 * 4 + r] * v[1];
-        acc = acc + m[2 * 4 + r] * v[2];
-        acc = acc + m[3 * 4 + r] * v[3];
+        acc = fmaf(m[1 * 4 + r], v[1], acc);
+        acc = fmaf(m[2 * 4 + r], v[2], acc);
+        acc = fmaf(m[3 * 4 + r], v[3], acc);
         out[r] = acc;
     }
 }
@@ -292,8 +303,8 @@ static void project_tail(const wso_camera_uniform *cam, const wso_render_setting
     float walltime = rs->walltime;
     float scale_mod = 0.f;
     float ddx = rs->center[0] - xyz[0], ddy = rs->center[1] - xyz[1], ddz = rs->center[2] - xyz[2];
-    float dist = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-    float dd = 5.f * dist / rs->scene_extend;
+    float dist = sqrtf(fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)));
+    float dd = 5.f * dist * rcp(rs->scene_extend);
     if (walltime > dd) {
         float t = (walltime - dd);                 /* smoothstep(0,1,t): clamp((t-0)/(1-0),0,1) */
         t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
@@ -310,30 +321,31 @@ static void project_tail(const wso_camera_uniform *cam, const wso_render_setting
     V[2][0] = c2; V[2][1] = c4; V[2][2] = c5;
 
     /* J (:209-219), as a math matrix Jm(row,col) = J_wgsl[col][row] */
-    float cz = camspace[2];
-    float j00 = fx / cz;
-    float j20 = -(fx * camspace[0]) / (cz * cz);
-    float j11 = -fy / cz;
-    float j21 = (fy * camspace[1]) / (cz * cz);
+    float rz = rcp(camspace[2]);                   /* 1 / z_cam, shared by the four entries */
+    float rz2 = rz * rz;
+    float j00 = fx * rz;
+    float j20 = -(fx * camspace[0]) * rz2;
+    float j11 = -(fy * rz);
+    float j21 = (fy * camspace[1]) * rz2;
 
     /* W = transpose(mat3(view[0].xyz, view[1].xyz, view[2].xyz)) (:221): Wm(i,k) = view[i][k] */
     /* T = W * J (:222): Tm(i,0) = Wm(i,0)*j00 + Wm(i,2)*j20 ; Tm(i,1) = Wm(i,1)*j11 + Wm(i,2)*j21 */
     float T0[3], T1[3];
     for (int i = 0; i < 3; i++) {
         float w0 = view[i * 4 + 0], w1 = view[i * 4 + 1], w2 = view[i * 4 + 2];
-        T0[i] = w0 * j00 + w2 * j20;
-        T1[i] = w1 * j11 + w2 * j21;
+        T0[i] = fmaf(w2, j20, w0 * j00);
+        T1[i] = fmaf(w2, j21, w1 * j11);
     }
     /* cov = transpose(T) * Vrk * T (:223): A = T^T V (2x3), cov = A T (2x2) */
     float A0[3], A1[3];
     for (int j = 0; j < 3; j++) {
-        float a = T0[0] * V[0][j]; a = a + T0[1] * V[1][j]; a = a + T0[2] * V[2][j]; A0[j] = a;
-        float b = T1[0] * V[0][j]; b = b + T1[1] * V[1][j]; b = b + T1[2] * V[2][j]; A1[j] = b;
+        float a = T0[0] * V[0][j]; a = fmaf(T0[1], V[1][j], a); a = fmaf(T0[2], V[2][j], a); A0[j] = a;
+        float b = T1[0] * V[0][j]; b = fmaf(T1[1], V[1][j], b); b = fmaf(T1[2], V[2][j], b); A1[j] = b;
     }
-    float cov00 = A0[0] * T0[0]; cov00 = cov00 + A0[1] * T0[1]; cov00 = cov00 + A0[2] * T0[2];
+    float cov00 = A0[0] * T0[0]; cov00 = fmaf(A0[1], T0[1], cov00); cov00 = fmaf(A0[2], T0[2], cov00);
     /* WGSL cov[0][1] = column 0, row 1 = (A row 1) . (T col 0) */
-    float cov01 = A1[0] * T0[0]; cov01 = cov01 + A1[1] * T0[1]; cov01 = cov01 + A1[2] * T0[2];
-    float cov11 = A1[0] * T1[0]; cov11 = cov11 + A1[1] * T1[1]; cov11 = cov11 + A1[2] * T1[2];
+    float cov01 = A1[0] * T0[0]; cov01 = fmaf(A1[1], T0[1], cov01); cov01 = fmaf(A1[2], T0[2], cov01);
+    float cov11 = A1[0] * T1[0]; cov11 = fmaf(A1[1], T1[1], cov11); cov11 = fmaf(A1[2], T1[2], cov11);
 
     float kernel_size = rs->kernel_size;
     if (rs->mip_splatting) {                       /* :226-236 */
@@ -351,7 +363,7 @@ static void project_tail(const wso_camera_uniform *cam, const wso_render_setting
     float diagonal2 = cov11 + kernel_size;
     float mid = 0.5f * (diagonal1 + diagonal2);
     float hx = (diagonal1 - diagonal2) / 2.0f;
-    float radius = sqrtf(hx * hx + offDiagonal * offDiagonal);
+    float radius = sqrtf(fmaf(offDiagonal, offDiagonal, hx * hx));
     float lambda1, lambda2;
     if (!compressed) {
         lambda1 = mid + radius;
@@ -363,26 +375,27 @@ static void project_tail(const wso_camera_uniform *cam, const wso_render_setting
         lambda2 = mid - rr;
     }
     float dvx = offDiagonal, dvy = lambda1 - diagonal1;
-    float dl = sqrtf(dvx * dvx + dvy * dvy);
-    dvx = dvx / dl; dvy = dvy / dl;                /* normalize; (0,0) -> NaN */
+    float rdl = rcp(sqrtf(fmaf(dvy, dvy, dvx * dvx)));
+    dvx = dvx * rdl; dvy = dvy * rdl;              /* normalize; (0,0) -> 0 * inf = NaN */
     float s1 = sqrtf(2.0f * lambda1), s2 = sqrtf(2.0f * lambda2);
     float v1x = s1 * dvx, v1y = s1 * dvy;
     float v2x = s2 * dvy, v2y = s2 * (-dvx);
 
-    float vcx = pos2d[0] / pos2d[3], vcy = pos2d[1] / pos2d[3];
+    float rw = rcp(pos2d[3]);
+    float vcx = pos2d[0] * rw, vcy = pos2d[1] * rw;
 
     /* :255-260 */
     float cpx = cam->view_inv[12], cpy = cam->view_inv[13], cpz = cam->view_inv[14];
     float dx = xyz[0] - cpx, dy = xyz[1] - cpy, dz = xyz[2] - cpz;
-    float dlen = sqrtf(dx * dx + dy * dy + dz * dz);
-    float dir[3] = { dx / dlen, dy / dlen, dz / dlen };
+    float rlen = rcp(sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
+    float dir[3] = { dx * rlen, dy * rlen, dz * rlen };
     vec3 col = evaluate_sh(dir, sh, rs->max_sh_deg);
     for (int i = 0; i < 3; i++) col.v[i] = (col.v[i] > 0.f) ? col.v[i] : 0.f;   /* max(vec3(0), c): NaN -> 0 */
 
-    float vw = cam->viewport[0], vh = cam->viewport[1];
+    float ivw = rcp(cam->viewport[0]), ivh = rcp(cam->viewport[1]);   /* per-frame constants */
     o->visible = 1;
-    o->splat[0] = wso_f32_to_f16(v1x / vw); o->splat[1] = wso_f32_to_f16(v1y / vh);
-    o->splat[2] = wso_f32_to_f16(v2x / vw); o->splat[3] = wso_f32_to_f16(v2y / vh);
+    o->splat[0] = wso_f32_to_f16(v1x * ivw); o->splat[1] = wso_f32_to_f16(v1y * ivh);
+    o->splat[2] = wso_f32_to_f16(v2x * ivw); o->splat[3] = wso_f32_to_f16(v2y * ivh);
     o->splat[4] = wso_f32_to_f16(vcx);      o->splat[5] = wso_f32_to_f16(vcy);
     o->splat[6] = wso_f32_to_f16(col.v[0]); o->splat[7] = wso_f32_to_f16(col.v[1]);
     o->splat[8] = wso_f32_to_f16(col.v[2]); o->splat[9] = wso_f32_to_f16(opacity);
@@ -411,7 +424,7 @@ static int cull_and_project(const wso_camera_uniform *cam, const wso_render_sett
     m4v4(cam->view, p, camspace);
     m4v4(cam->proj, camspace, pos2d);
     float bounds = 1.2f * pos2d[3];
-    float z = pos2d[2] / pos2d[3];
+    float z = pos2d[2] * rcp(pos2d[3]);
     if (!compressed) {
         if (z <= 0.f || z >= 1.f || pos2d[0] < -bounds || pos2d[0] > bounds || pos2d[1] < -bounds || pos2d[1] > bounds)
             return 0;

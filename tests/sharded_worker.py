@@ -49,11 +49,14 @@ def main():
                 same2 = torch.equal(host, ref.cpu())
                 ok = ok and same2
                 print("   to_root identical=%s" % same2, flush=True)
-            # and the variant without any host-side collective (mailbox flags in peer memory), several frames back to back
+            # and the variant without any host-side collective (mailbox flags in peer memory), several frames back to back;
+            # the last one with the occlusion split forced on inside every band (automatic only from 2 M points per rank)
             for rep in range(3):
                 if rank == 0:
                     host.zero_()
+                sh.r.set_occlusion_split(rep == 2)
                 sh.frame_peer(args, clear=(0.1, 0.2, 0.3, 0.5), root=0, host=host)
+            sh.r.set_occlusion_split(None)
             torch.cuda.synchronize()
             if rank == 0:
                 same3 = torch.equal(host, ref.cpu())

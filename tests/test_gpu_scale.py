@@ -102,10 +102,21 @@ def test_cfg4_full_size_compressed_4k(ws, orc, ctx):
     assert np.array_equal(r.read_buffer(ws.BUF_DEPTH_KEYS), okeys)
     assert np.abs(f16_ordered(splats) - f16_ordered(osplats))[:, 4:].max() <= 1
     a = splats.view(np.float16).astype(np.float64); b = osplats.view(np.float16).astype(np.float64)
+    # Axes: a 1-ulp difference in expf can swing the eigenvector of a nearly isotropic splat by a large angle
+    # (normalize((off, l1 - d1)) with both components tiny, preprocess_compressed.wgsl:299) without changing the
+    # footprint, so every splat is compared through the 2x2 covariance its axes span, v1 v1^T + v2 v2^T (pixels^2),
+    # and the axes themselves, as vectors, on all but the ill-conditioned few
+    pa, pb = a[:, :4] * [W, H, W, H], b[:, :4] * [W, H, W, H]
+    def cov(p_):
+        return np.stack([p_[:, 0] ** 2 + p_[:, 2] ** 2, p_[:, 0] * p_[:, 1] + p_[:, 2] * p_[:, 3], p_[:, 1] ** 2 + p_[:, 3] ** 2], 1)
+    ca, cb = cov(pa), cov(pb)
+    fin = np.isfinite(cb).all(1)
+    assert np.array_equal(fin, np.isfinite(ca).all(1))
+    assert (np.abs(ca - cb)[fin].max(1) <= 1e-2 * np.abs(cb)[fin].max(1) + 1e-3).all()
     for sl in (slice(0, 2), slice(2, 4)):
-        na = np.linalg.norm(b[:, sl] * [W, H], axis=1)
-        err = np.linalg.norm((a[:, sl] - b[:, sl]) * [W, H], axis=1)
-        assert (err <= 4e-3 * na + 1e-3).all()
+        na = np.linalg.norm(pb[:, sl], axis=1)
+        err = np.linalg.norm(pa[:, sl] - pb[:, sl], axis=1)
+        assert (err[fin] <= 4e-3 * na[fin] + 1e-3).mean() > 0.999
     sk, order = orc.sort_pairs(okeys, np.arange(V, dtype=np.uint32))
     assert np.array_equal(r.read_buffer(ws.BUF_SORTED_KEYS), sk)
     assert np.array_equal(r.read_buffer(ws.BUF_SORTED_INDICES), order)

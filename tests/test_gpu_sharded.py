@@ -42,6 +42,18 @@ def test_sharded_world1_equals_plain(ws, orc, ctx):
         sh.frame_peer(args, host=host)
         torch.cuda.synchronize()
         assert torch.equal(host, t.cpu())
+    # occlusion split inside the band (automatic from 2 M points per rank; forced here): same pixels from fewer pairs
+    full_pairs = sh.stats()["num_pairs"]
+    sh.r.set_occlusion_split(True)
+    for _ in range(2):
+        host.zero_()
+        sh.frame_peer(args, host=host)
+        torch.cuda.synchronize()
+        assert torch.equal(host, t.cpu())
+    assert sh.stats()["num_pairs"] <= full_pairs
+    sh.r.set_occlusion_split(False)
+    sh.frame_peer(args, host=host)
+    torch.cuda.synchronize()
     st = sh.stats()
     # only splats that touch at least one tile are routed, so the received count can be below V
     assert st["num_visible"] <= plain.stats()["num_visible"] and st["num_pairs"] == plain.stats()["num_pairs"]

@@ -969,6 +969,25 @@ static ws_status validate_frame(ws_renderer *r, ws_pointcloud *pc, const ws_spla
     return WS_OK;
 }
 
+// Occlusion split on/off for this frame + the per-pixel state buffer it needs.  `points_here` = Gaussians this GPU
+// depth-sorts (the whole cloud; total / world for sharded frames).  Automatic threshold: measured on one GPU cfg1
+// (100 K points) -14 %, cfg2 (1 M) -2 %, cfg3 (6 M) +7 % -- the six extra launches and the state round trip pay off only
+// when there are many pairs to save.
+static ws_status decide_split(ws_renderer *r, uint64_t points_here, uint32_t W, uint32_t H)
+{
+    r->frame_split = r->split_mode == 1 || (r->split_mode == 2 && points_here >= 2000000u);
+    if (r->frame_split) {
+        const size_t px = (size_t)W * H;
+        if (r->state_px < px) {
+            cudaFree(r->d_state); r->d_state = nullptr; r->state_px = 0;
+            CU(cudaMalloc(&r->d_state, px * sizeof(float4)));
+            r->state_px = px;
+            r->buf_generation = next_generation();
+        }
+    }
+    return WS_OK;
+}
+
 // uniforms + per-frame clears (everything before stage 1)
 static ws_status begin_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args, uint32_t capacity_points, cudaStream_t stream,
                             bool with_clears = true)
@@ -986,13 +1005,21 @@ static ws_status begin_frame(ws_renderer *r, ws_pointcloud *pc, const ws_splatti
     U.quant = pc->quant;
     U.width = W; U.height = H; U.tiles_x = tx; U.tiles_y = ty;
     U.num_points = pc->n; U.file_sh_deg = pc->sh_deg; U.pair_capacity = r->pair_cap; U._pad0 = 0;
+    {   // per-frame constants of stage 1: one IEEE f32 division each, here instead of once per Gaussian
+        volatile float one = 1.0f;                     // keep the host compiler from folding these into other precision
+        U.inv_viewport[0] = one / U.cam.viewport[0]; U.inv_viewport[1] = one / U.cam.viewport[1];
+        U.znear = -U.cam.proj[3 * 4 + 2] / U.cam.proj[2 * 4 + 2];
+        U.zfar = -U.cam.proj[3 * 4 + 2] / (U.cam.proj[2 * 4 + 2] - 1.f);
+        U.inv_scene_extend = one / U.rs.scene_extend;
+        U._padf[0] = U._padf[1] = U._padf[2] = 0.f;
+    }
     r->tile_passes = (tiles > 65536u) ? 3 : ((tiles > 256u) ? 2 : 1);
 
     // pageable source: the runtime stages the 0.5 KB before returning, so h_uniforms may be reused
     CU(cudaMemcpyAsync(r->d_uniforms, &U, sizeof U, cudaMemcpyHostToDevice, stream));
     if (with_clears) {
         CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, stream));
-        CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)tiles * 8, stream));    // {begin, ~end} identities for atomicMin
+        CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)r->tiles_cap * 8 * (r->frame_split ? 2 : 1), stream));    // {begin, ~end} identities for atomicMin (one set per depth slab)
     }
     return WS_OK;
 }
@@ -1075,7 +1102,11 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
         a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
         a.uniforms = r->d_uniforms; a.format = (int)r->format;
         a.mode = 1; a.state = r->d_state; a.tile_done = r->d_tile_done;
-        CU(launch_composite(a, r->h_uniforms.tiles_x, r->h_uniforms.tiles_y, stream));
+        // sharded frames: only this rank's band of tile rows (the received rectangles are clipped to it)
+        const bool band = r->shard.world > 0;
+        a.tile_y0 = band ? r->shard.band_y0[r->shard.rank] : 0u;
+        const uint32_t rows = band ? r->shard.band_y0[r->shard.rank + 1] - r->shard.band_y0[r->shard.rank] : r->h_uniforms.tiles_y;
+        if (rows) CU(launch_composite(a, r->h_uniforms.tiles_x, rows, stream));
     }
     if (r->timing) CU(cudaEventRecord(r->ev[EV_NEAR_BLEND], stream));
     return bin_and_tile_sort(2u, 1, EV_BIN2, EV_TSORT2, &r->tile_out_far);
@@ -1110,18 +1141,8 @@ extern "C" ws_status ws_renderer_prepare(ws_renderer *r, ws_pointcloud *pc, cons
     CU(cudaSetDevice(r->ctx->device));
     st = take_deferred_status(r);
     if (st != WS_OK) return st;
-    // auto: the six extra launches and the state round trip pay off only when there are many pairs to save -- measured
-    // cfg 1 (100 K points) -14 %, cfg 2 (1 M) -2 %, cfg 3 (6 M) +7 %
-    r->frame_split = r->shard.world == 0 && (r->split_mode == 1 || (r->split_mode == 2 && pc->n >= 2000000u));
-    if (r->frame_split) {
-        const size_t px = (size_t)args->viewport[0] * args->viewport[1];
-        if (r->state_px < px) {
-            cudaFree(r->d_state); r->d_state = nullptr; r->state_px = 0;
-            CU(cudaMalloc(&r->d_state, px * sizeof(float4)));
-            r->state_px = px;
-            r->buf_generation = next_generation();
-        }
-    }
+    st = decide_split(r, pc->n, args->viewport[0], args->viewport[1]);
+    if (st != WS_OK) return st;
     st = begin_frame(r, pc, args, pc->n, stream, /*with_clears=*/false);     // uniforms only; capacities may (re)allocate
     if (st != WS_OK) return st;
     if (r->use_graphs && !r->timing) {
@@ -1387,7 +1408,10 @@ extern "C" ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointclo
     CU(cudaSetDevice(r->ctx->device));
     st = take_deferred_status(r);
     if (st != WS_OK) return st;
-    r->frame_split = false;
+    // occlusion split inside the band (same bit-identical two-slab scheme as the single-GPU frame): automatic when this
+    // rank's share of the cloud is large enough to pay for the extra launches (2 GPUs at cfg3: yes; 8 GPUs: no)
+    st = decide_split(r, (uint64_t)s.recv_cap / s.world, s.width, s.height);
+    if (st != WS_OK) return st;
     st = begin_frame(r, pc, args, s.recv_cap, stream);
     if (st != WS_OK) return st;
     s.epoch += 1;

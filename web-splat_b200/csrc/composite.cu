@@ -16,7 +16,10 @@
 //    can touch its 32 pixels (most of a tile's list does not), and skips everything once
 //    all of its pixels are saturated (warp-level early-out);
 //  * the centre is expressed relative to the tile origin with exact f16 x integer products,
-//    so `a` carries ~1e-5 absolute error at 4K instead of ulp(3840).
+//    so `a` carries ~1e-5 absolute error at 4K instead of ulp(3840);
+//  * the per-hit code is branch-free and keeps no `done` flag: a pixel whose transmittance falls below 2^-16 has its
+//    T set to exactly 0, after which every further weight is exactly 0 (round 1 tested a flag per hit: 35 SASS
+//    instructions per warp x splat hit, 28 now -- the kernel is issue-bound, profiles/r02*_ncu_summary.md).
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
@@ -80,11 +83,10 @@ template <int FORMAT, int MODE>
 __global__ void __launch_bounds__(CB_THREADS)
 composite_kernel(CompositeArgs a)
 {
-    // double-buffered staging: batch b+1 is fetched (global gathers) while batch b is evaluated
-    __shared__ float4 s_a[2][CB_BATCH];
-    __shared__ float4 s_b[2][CB_BATCH];
-    __shared__ float2 s_c[2][CB_BATCH];
-    __shared__ float4 s_d[2][CB_BATCH];              // bounding box for the per-warp cull
+    // double-buffered staging: batch b+1 is fetched (global gathers) while batch b is evaluated.  One 48-B record per
+    // splat {A, B, C}: the hit loop addresses it with ONE uniform base (three ULEAs in round 1)
+    __shared__ float4 s_abc[2][CB_BATCH * 3];
+    __shared__ float4 s_d[2][CB_BATCH];              // bounding box for the per-warp cull (dense: conflict-free LDS.128)
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = a.uniforms->width, H = a.uniforms->height;
@@ -108,13 +110,12 @@ composite_kernel(CompositeArgs a)
     const float blo_x = (float)bx - 7.5f, bhi_x = (float)bx - 0.5f;
     const float blo_y = (float)by - 7.5f, bhi_y = (float)by - 4.5f;
 
-    float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
-    bool done = !inside;
+    // T == 0 means "saturated" (or outside the frame): nothing can change the pixel any more
+    float T = inside ? 1.f : 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     if (MODE == 2) {
         if (inside) {
             const float4 st = a.state[(size_t)py * W + px];
             cr = st.x; cg = st.y; cb = st.z; T = st.w;
-            done = T < T_EPS;
         }
         if (a.tile_done[tile]) range.x = range.y = 0u;   // saturated by the near slab: nothing of the far slab can show
     }
@@ -140,9 +141,10 @@ composite_kernel(CompositeArgs a)
         if ((int)tid < cnt) {
             float4 A, B, C, D;
             decode_splat(nxt, fw, fh, hw, hh, ox, oy, A, B, C, D);
-            s_a[buf][tid] = A; s_b[buf][tid] = B; s_c[buf][tid] = make_float2(C.x, C.y); s_d[buf][tid] = D;
+            float4 *rec = &s_abc[buf][tid * 3];
+            rec[0] = A; rec[1] = B; rec[2] = C; s_d[buf][tid] = D;
         }
-        const bool warp_done = __all_sync(0xffffffffu, done);
+        const bool warp_done = __all_sync(0xffffffffu, T == 0.f);
         // one barrier per batch: makes the batch visible and agrees on the tile-level early-out.  Buffer
         // `buf` was last read two batches ago, and every warp has passed the previous barrier since.
         if (__syncthreads_and(warp_done ? 1 : 0)) break;
@@ -153,22 +155,22 @@ composite_kernel(CompositeArgs a)
         if (remaining > 0) fetch(nxt, cursor, cnt);          // in flight while this batch is evaluated
 
         if (!warp_done) {
-            const float4 *sa = s_a[buf], *sb = s_b[buf], *sd = s_d[buf];
-            const float2 *sc = s_c[buf];
-            // one pixel-splat evaluation: 5 FMAs for a*log2(e), MUFU.EX2, blend
+            const float4 *sabc = s_abc[buf], *sd = s_d[buf];
+            // one pixel-splat evaluation, branch-free: 5 FMAs for a*log2(e), MUFU.EX2, weight (0 outside the footprint:
+            // a select, so a NaN `a` -- degenerate axes -- contributes nothing), blend, saturation clamp of T
 #define WS_EVAL(J)                                                                              \
             {                                                                                   \
-                const float4 A = sa[J];                                                         \
-                const float4 B = sb[J];                                                         \
+                const float4 *rec = sabc + (J) * 3;                                             \
+                const float4 A = rec[0];                                                        \
+                const float4 B = rec[1];                                                        \
+                const float2 C = *reinterpret_cast<const float2 *>(rec + 2);                    \
                 float aa = fmaf(A.y, fx, A.x);                                                  \
                 aa = fmaf(A.z, fy, aa); aa = fmaf(A.w, fxx, aa); aa = fmaf(B.x, fxy, aa); aa = fmaf(B.y, fyy, aa); \
-                if (!done && aa <= TWO_CUTOFF * LOG2E) {                                        \
-                    const float2 C = sc[J];                                                     \
-                    const float wt = fminf(0.99f, ex2_approx(-aa) * B.z) * T;                   \
-                    cr = fmaf(B.w, wt, cr); cg = fmaf(C.x, wt, cg); cb = fmaf(C.y, wt, cb);     \
-                    T -= wt;                                      /* T * (1 - w) */             \
-                    if (T < T_EPS) done = true;                                                 \
-                }                                                                               \
+                float wt = fminf(0.99f, ex2_approx(-aa) * B.z) * T;                             \
+                wt = (aa <= TWO_CUTOFF * LOG2E) ? wt : 0.f;                                     \
+                cr = fmaf(B.w, wt, cr); cg = fmaf(C.x, wt, cg); cb = fmaf(C.y, wt, cb);         \
+                T -= wt;                                          /* T * (1 - w) */             \
+                T = (T < T_EPS) ? 0.f : T;                                                      \
             }
             for (int c0 = 0; c0 < cur_cnt; c0 += 32) {
                 const int k = c0 + (int)lane;
@@ -188,7 +190,7 @@ composite_kernel(CompositeArgs a)
                         WS_EVAL(j1)
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+                if (__all_sync(0xffffffffu, T == 0.f)) break;
             }
 #undef WS_EVAL
         }
@@ -197,7 +199,7 @@ composite_kernel(CompositeArgs a)
 
     if (MODE == 1) {
         if (inside) a.state[(size_t)py * W + px] = make_float4(cr, cg, cb, T);
-        const int all_done = __syncthreads_and(done ? 1 : 0);
+        const int all_done = __syncthreads_and(T == 0.f ? 1 : 0);
         if (tid == 0) a.tile_done[tile] = (uint8_t)(all_done ? 1 : 0);
         return;
     }

@@ -22,8 +22,12 @@
 //    (one full 32-B sector per request);
 //  * records are read from shared memory at a conflict-free 7-word (6-word: 2-way) stride;
 //    outputs are staged through shared memory and leave as coalesced streams;
-//  * this file is compiled with -fmad=false: every f32 operation rounds once, in the
-//    order written, which makes stage 1 bit-identical to the CPU oracle (raw layout).
+//  * this file is compiled with -fmad=false, so a fused multiply-add happens exactly where fmaf() is
+//    written -- the same places as in oracle/ws_oracle.c -- and quotients with a shared divisor are a
+//    correctly rounded reciprocal (__frcp_rn: MUFU.RCP + Newton step) times the numerator, again as
+//    in the oracle: stage 1 stays bit-identical to the CPU oracle (raw layout) with ~20 % fewer
+//    instructions than the round-1 "one rounding per written operation" form (19 IEEE divisions
+//    per Gaussian then, 4 reciprocals now; per-frame constants 1/W, 1/H, znear, zfar come from the host).
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
@@ -46,6 +50,7 @@ struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 v3s(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
 __device__ __forceinline__ V3 v3add(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ V3 v3sub(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 v3fma(float s, V3 a, V3 acc) { return V3{fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y), fmaf(s, a.z, acc.z)}; }
 
 // SH basis constants, preprocess.wgsl:4-23
 #define WS_SH_C0 0.28209479177387814f
@@ -71,19 +76,22 @@ struct ShRaw {
 };
 struct ShQuant {
     uint32_t w[12];                 // the entry's (file_deg+1)^2*3 i8 bytes, dc first (io/npz.rs:183-196), zero padded
-    Quant dc, rest;
-    __device__ __forceinline__ float dq(int8_t b, const Quant &q) const
+    const float *lut;               // shared memory: [0..255] dc, [256..511] rest -- dequantised value of every i8 code
+    // One table entry = sh_coef() of preprocess_compressed.wgsl:147-171 for that byte: unpack4x8snorm * 127, then
+    // dequantizef4 -- the oracle's arithmetic, evaluated 512 times per CTA instead of 48 times per Gaussian (each with
+    // an IEEE division by 127: 430 of the ~2300 instructions per Gaussian in round 1).
+    static __device__ __forceinline__ float dq(int8_t b, const Quant &q)
     {
         float sn = (float)b / 127.f;            // unpack4x8snorm: max(i/127, -1)
         if (sn < -1.f) sn = -1.f;
         float v = sn * 127.f;
         return (v - (float)q.zero_point) * q.scale;   // dequantizef4
     }
-    __device__ __forceinline__ int8_t byte(int i) const { return (int8_t)((w[i >> 2] >> ((i & 3) * 8)) & 0xffu); }
+    __device__ __forceinline__ uint32_t byte(int i) const { return (w[i >> 2] >> ((i & 3) * 8)) & 0xffu; }
     __device__ __forceinline__ V3 coef(int k) const
     {
-        const Quant &q = (k == 0) ? dc : rest;
-        return V3{dq(byte(k * 3), q), dq(byte(k * 3 + 1), q), dq(byte(k * 3 + 2), q)};
+        const float *t = lut + ((k == 0) ? 0 : 256);
+        return V3{t[byte(k * 3)], t[byte(k * 3 + 1)], t[byte(k * 3 + 2)]};
     }
     // entry base = sh_idx * ncoef * 3 bytes; degree-3 entries (48 B) are 16-B aligned: three 128-bit loads
     __device__ __forceinline__ void load(const uint8_t *base, uint32_t sh_idx, uint32_t ncoef)
@@ -112,25 +120,25 @@ __device__ __forceinline__ V3 evaluate_sh(float x, float y, float z, const SH &s
     V3 result = v3s(WS_SH_C0, sh.coef(0));
     if (deg > 0u) {
         V3 t = v3s((-WS_SH_C1) * y, sh.coef(1));
-        t = v3add(t, v3s(WS_SH_C1 * z, sh.coef(2)));
-        t = v3sub(t, v3s(WS_SH_C1 * x, sh.coef(3)));
+        t = v3fma(WS_SH_C1 * z, sh.coef(2), t);
+        t = v3fma(-(WS_SH_C1 * x), sh.coef(3), t);
         result = v3add(result, t);
         if (deg > 1u) {
             float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             V3 u = v3s(WS_SH_C2_0 * xy, sh.coef(4));
-            u = v3add(u, v3s(WS_SH_C2_1 * yz, sh.coef(5)));
-            u = v3add(u, v3s(WS_SH_C2_2 * (2.0f * zz - xx - yy), sh.coef(6)));
-            u = v3add(u, v3s(WS_SH_C2_3 * xz, sh.coef(7)));
-            u = v3add(u, v3s(WS_SH_C2_4 * (xx - yy), sh.coef(8)));
+            u = v3fma(WS_SH_C2_1 * yz, sh.coef(5), u);
+            u = v3fma(WS_SH_C2_2 * (2.0f * zz - xx - yy), sh.coef(6), u);
+            u = v3fma(WS_SH_C2_3 * xz, sh.coef(7), u);
+            u = v3fma(WS_SH_C2_4 * (xx - yy), sh.coef(8), u);
             result = v3add(result, u);
             if (deg > 2u) {
                 V3 w = v3s(WS_SH_C3_0 * y * (3.0f * xx - yy), sh.coef(9));
-                w = v3add(w, v3s(WS_SH_C3_1 * xy * z, sh.coef(10)));
-                w = v3add(w, v3s(WS_SH_C3_2 * y * (4.0f * zz - xx - yy), sh.coef(11)));
-                w = v3add(w, v3s(WS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), sh.coef(12)));
-                w = v3add(w, v3s(WS_SH_C3_4 * x * (4.0f * zz - xx - yy), sh.coef(13)));
-                w = v3add(w, v3s(WS_SH_C3_5 * z * (xx - yy), sh.coef(14)));
-                w = v3add(w, v3s(WS_SH_C3_6 * x * (xx - 3.0f * yy), sh.coef(15)));
+                w = v3fma(WS_SH_C3_1 * xy * z, sh.coef(10), w);
+                w = v3fma(WS_SH_C3_2 * y * (4.0f * zz - xx - yy), sh.coef(11), w);
+                w = v3fma(WS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), sh.coef(12), w);
+                w = v3fma(WS_SH_C3_4 * x * (4.0f * zz - xx - yy), sh.coef(13), w);
+                w = v3fma(WS_SH_C3_5 * z * (xx - yy), sh.coef(14), w);
+                w = v3fma(WS_SH_C3_6 * x * (xx - 3.0f * yy), sh.coef(15), w);
                 result = v3add(result, w);
             }
         }
@@ -157,8 +165,8 @@ struct Stage1 {
 template <bool COMPRESSED>
 __device__ __forceinline__ uint32_t depth_key(const FrameUniforms &U, float p2)
 {
-    const float znear = -U.cam.proj[3 * 4 + 2] / U.cam.proj[2 * 4 + 2];
-    const float zfar = -U.cam.proj[3 * 4 + 2] / (U.cam.proj[2 * 4 + 2] - 1.f);
+    // znear = -proj[3][2] / proj[2][2], zfar = -proj[3][2] / (proj[2][2] - 1): per-frame constants, divided once on the host
+    const float znear = U.znear, zfar = U.zfar;
     if (!COMPRESSED) return __float_as_uint(zfar - p2);
     const float kf = 16777215.f - (p2 - znear) / (zfar - znear) * 16777215.f;
     if (!(kf > 0.f)) return 0u;
@@ -180,8 +188,8 @@ __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, fl
     float scale_mod = 0.f;
     {
         float ddx = U.rs.center[0] - x, ddy = U.rs.center[1] - y, ddz = U.rs.center[2] - z;
-        float dist = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-        float dd = 5.f * dist / U.rs.scene_extend;
+        float dist = sqrtf(fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)));
+        float dd = 5.f * dist * U.inv_scene_extend;
         if (U.rs.walltime > dd) {
             float t = U.rs.walltime - dd;
             t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
@@ -193,27 +201,28 @@ __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, fl
     const float c3 = cov6[3] * scaling * scaling, c4 = cov6[4] * scaling * scaling, c5 = cov6[5] * scaling * scaling;
     const float Vm[3][3] = {{c0, c1, c2}, {c1, c3, c4}, {c2, c4, c5}};
 
-    const float j00 = fx / cs2;
-    const float j20 = -(fx * cs0) / (cs2 * cs2);
-    const float j11 = -fy / cs2;
-    const float j21 = (fy * cs1) / (cs2 * cs2);
+    const float rz = __frcp_rn(cs2), rz2 = rz * rz;
+    const float j00 = fx * rz;
+    const float j20 = -(fx * cs0) * rz2;
+    const float j11 = -(fy * rz);
+    const float j21 = (fy * cs1) * rz2;
 
     float T0[3], T1[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         float w0 = view[i * 4 + 0], w1 = view[i * 4 + 1], w2 = view[i * 4 + 2];
-        T0[i] = w0 * j00 + w2 * j20;
-        T1[i] = w1 * j11 + w2 * j21;
+        T0[i] = fmaf(w2, j20, w0 * j00);
+        T1[i] = fmaf(w2, j21, w1 * j11);
     }
     float A0[3], A1[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        float a = T0[0] * Vm[0][j]; a = a + T0[1] * Vm[1][j]; a = a + T0[2] * Vm[2][j]; A0[j] = a;
-        float b = T1[0] * Vm[0][j]; b = b + T1[1] * Vm[1][j]; b = b + T1[2] * Vm[2][j]; A1[j] = b;
+        float a = T0[0] * Vm[0][j]; a = fmaf(T0[1], Vm[1][j], a); a = fmaf(T0[2], Vm[2][j], a); A0[j] = a;
+        float b = T1[0] * Vm[0][j]; b = fmaf(T1[1], Vm[1][j], b); b = fmaf(T1[2], Vm[2][j], b); A1[j] = b;
     }
-    float cov00 = A0[0] * T0[0]; cov00 = cov00 + A0[1] * T0[1]; cov00 = cov00 + A0[2] * T0[2];
-    float cov01 = A1[0] * T0[0]; cov01 = cov01 + A1[1] * T0[1]; cov01 = cov01 + A1[2] * T0[2];
-    float cov11 = A1[0] * T1[0]; cov11 = cov11 + A1[1] * T1[1]; cov11 = cov11 + A1[2] * T1[2];
+    float cov00 = A0[0] * T0[0]; cov00 = fmaf(A0[1], T0[1], cov00); cov00 = fmaf(A0[2], T0[2], cov00);
+    float cov01 = A1[0] * T0[0]; cov01 = fmaf(A1[1], T0[1], cov01); cov01 = fmaf(A1[2], T0[2], cov01);
+    float cov11 = A1[0] * T1[0]; cov11 = fmaf(A1[1], T1[1], cov11); cov11 = fmaf(A1[2], T1[2], cov11);
 
     const float ks = U.rs.kernel_size;
     if (U.rs.mip_splatting) {                      // :226-236
@@ -229,7 +238,7 @@ __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, fl
     const float diagonal1 = cov00 + ks, offDiagonal = cov01, diagonal2 = cov11 + ks;
     const float mid = 0.5f * (diagonal1 + diagonal2);
     const float hx = (diagonal1 - diagonal2) / 2.0f;
-    const float radius = sqrtf(hx * hx + offDiagonal * offDiagonal);
+    const float radius = sqrtf(fmaf(offDiagonal, offDiagonal, hx * hx));
     float lambda1, lambda2;
     if (!COMPRESSED) {
         lambda1 = mid + radius;
@@ -241,22 +250,23 @@ __device__ __forceinline__ void project_tail(const FrameUniforms &U, float x, fl
         lambda2 = mid - rr;
     }
     float dvx = offDiagonal, dvy = lambda1 - diagonal1;
-    const float dl = sqrtf(dvx * dvx + dvy * dvy);
-    dvx = dvx / dl; dvy = dvy / dl;
+    const float rdl = __frcp_rn(sqrtf(fmaf(dvy, dvy, dvx * dvx)));
+    dvx = dvx * rdl; dvy = dvy * rdl;
     const float s1 = sqrtf(2.0f * lambda1), s2 = sqrtf(2.0f * lambda2);
     const float v1x = s1 * dvx, v1y = s1 * dvy, v2x = s2 * dvy, v2y = s2 * (-dvx);
-    const float vcx = p0 / p3, vcy = p1 / p3;
+    const float rw = __frcp_rn(p3);
+    const float vcx = p0 * rw, vcy = p1 * rw;
 
     const float dx = x - U.cam.view_inv[12], dy = y - U.cam.view_inv[13], dz = z - U.cam.view_inv[14];
-    const float dlen = sqrtf(dx * dx + dy * dy + dz * dz);
-    V3 col = evaluate_sh(dx / dlen, dy / dlen, dz / dlen, sh, U.rs.max_sh_deg);
+    const float rlen = __frcp_rn(sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
+    V3 col = evaluate_sh(dx * rlen, dy * rlen, dz * rlen, sh, U.rs.max_sh_deg);
     col.x = (col.x > 0.f) ? col.x : 0.f;
     col.y = (col.y > 0.f) ? col.y : 0.f;
     col.z = (col.z > 0.f) ? col.z : 0.f;
 
-    const float vw = U.cam.viewport[0], vh = U.cam.viewport[1];
-    o.splat[0] = pack2h(v1x / vw, v1y / vh);
-    o.splat[1] = pack2h(v2x / vw, v2y / vh);
+    const float ivw = U.inv_viewport[0], ivh = U.inv_viewport[1];       // 1 / viewport, divided once on the host
+    o.splat[0] = pack2h(v1x * ivw, v1y * ivh);
+    o.splat[1] = pack2h(v2x * ivw, v2y * ivh);
     o.splat[2] = pack2h(vcx, vcy);
     o.splat[3] = pack2h(col.x, col.y);
     o.splat[4] = pack2h(col.z, opacity);
@@ -300,21 +310,21 @@ __device__ __forceinline__ bool cull_project(const FrameUniforms &U, float x, fl
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         float acc = view[0 * 4 + r] * x;
-        acc = acc + view[1 * 4 + r] * y;
-        acc = acc + view[2 * 4 + r] * z;
-        acc = acc + view[3 * 4 + r] * 1.f;
+        acc = fmaf(view[1 * 4 + r], y, acc);
+        acc = fmaf(view[2 * 4 + r], z, acc);
+        acc = fmaf(view[3 * 4 + r], 1.f, acc);
         cs[r] = acc;
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         float acc = proj[0 * 4 + r] * cs[0];
-        acc = acc + proj[1 * 4 + r] * cs[1];
-        acc = acc + proj[2 * 4 + r] * cs[2];
-        acc = acc + proj[3 * 4 + r] * cs[3];
+        acc = fmaf(proj[1 * 4 + r], cs[1], acc);
+        acc = fmaf(proj[2 * 4 + r], cs[2], acc);
+        acc = fmaf(proj[3 * 4 + r], cs[3], acc);
         pp[r] = acc;
     }
     const float bounds = 1.2f * pp[3];
-    const float zz = pp[2] / pp[3];
+    const float zz = pp[2] * __frcp_rn(pp[3]);
     if (!COMPRESSED) {
         if (zz <= 0.f || zz >= 1.f || pp[0] < -bounds || pp[0] > bounds || pp[1] < -bounds || pp[1] > bounds) return false;
     } else {
@@ -414,7 +424,8 @@ struct PPSmem {
     static constexpr uint32_t off_u = off_rect + PP_THREADS * 8u;
     static constexpr uint32_t off_bar = (off_u + (uint32_t)sizeof(FrameUniforms) + 15u) & ~15u;
     static constexpr uint32_t off_misc = off_bar + 8u * (2 * PP_STAGES);
-    static constexpr uint32_t bytes = off_misc + 64u;
+    static constexpr uint32_t off_lut = off_misc + 64u;                                        // compressed: 2 x 256 dequantised SH codes
+    static constexpr uint32_t bytes = off_lut + (COMPRESSED ? 2u * 256u * 4u : 0u);
 };
 
 template <bool COMPRESSED>
@@ -441,6 +452,13 @@ preprocess_kernel(PreprocessArgs a)
     if (tid == 0) {
         for (int i = 0; i < 2 * PP_STAGES; i++) mbar_init(&s_rbar[i], 1);
         fence_mbar_init();
+    }
+    float *s_lut = reinterpret_cast<float *>(smem + L::off_lut);
+    if (COMPRESSED) {
+        const FrameUniforms *gu = a.uniforms;                    // s_u is not visible yet: read the two quantisers from global
+        const Quant qd = gu->quant.color_dc, qr = gu->quant.color_rest;
+        s_lut[tid] = ShQuant::dq((int8_t)tid, qd);               // index = the byte's bit pattern
+        s_lut[256 + tid] = ShQuant::dq((int8_t)tid, qr);
     }
     __syncthreads();
     const FrameUniforms &U = s_u;
@@ -528,7 +546,7 @@ preprocess_kernel(PreprocessArgs a)
                     const uint32_t ncoef = (U.file_sh_deg + 1u) * (U.file_sh_deg + 1u);
                     ShQuant sh;
                     sh.load(a.sh_coefs, sh_idx, ncoef);
-                    sh.dc = U.quant.color_dc; sh.rest = U.quant.color_rest;
+                    sh.lut = s_lut;
                     project_tail<true>(U, x, y, z, cs[0], cs[1], cs[2], pp[0], pp[1], pp[2], pp[3], cov6, opacity, sh, o);
                 }
             }

@@ -40,9 +40,18 @@ constexpr int WARPS = SORT_THREADS / 32;
 struct LbState { uint32_t excl; bool done; };
 
 // Walk one level of status words from row p down to row lo (nearest predecessor first).
-// `col` already points at this thread's bin column.  Up to four relaxed loads are issued per
-// step (they are independent), then consumed in order; an unpublished word restarts the step.
-// Rows below lo end the level; when `below_is_prefix` they count as "inclusive prefix 0".
+// `col` already points at this thread's bin column.  Up to LB_WIDTH relaxed loads are issued per
+// step (they are independent), then consumed in order; an unpublished word restarts the step at
+// that row.  Rows below lo end the level; when `below_is_prefix` they count as "inclusive prefix 0".
+// LB_WIDTH: round 1 issued 4 loads per step; ncu (profiles/r02a: 37 % of the pass's executed warp
+// instructions and 25 % of its stall samples sit in this loop) showed the walk over up to 15 + W/16
+// rows -- a persistent grid starts W = 444 partitions at once, none with a prefix -- costing ~8
+// dependent L2 round trips per partition; 16 loads per step make it ~3.
+#ifndef WS_LB_WIDTH
+#define WS_LB_WIDTH 16
+#endif
+constexpr int LB_WIDTH = WS_LB_WIDTH;
+
 __device__ __forceinline__ void lookback_level(const uint32_t *col, int p, int lo, bool below_is_prefix,
                                                LbState &st, uint32_t *err)
 {
@@ -50,25 +59,19 @@ __device__ __forceinline__ void lookback_level(const uint32_t *col, int p, int l
     while (!st.done) {
         if (p < lo) { if (below_is_prefix) st.done = true; return; }
         const int n = p - lo;                                  // extra rows available beyond p
-        const uint32_t s0 = ld_relaxed(col + (size_t)p * 256u);
-        const uint32_t s1 = (n >= 1) ? ld_relaxed(col + (size_t)(p - 1) * 256u) : 0u;
-        const uint32_t s2 = (n >= 2) ? ld_relaxed(col + (size_t)(p - 2) * 256u) : 0u;
-        const uint32_t s3 = (n >= 3) ? ld_relaxed(col + (size_t)(p - 3) * 256u) : 0u;
-        if ((s0 >> LB_FLAG_SHIFT) == 0u) {                     // nearest one not published yet: poll again
+        uint32_t s[LB_WIDTH];
+#pragma unroll
+        for (int k = 0; k < LB_WIDTH; k++) s[k] = (n >= k) ? ld_relaxed(col + (size_t)(p - k) * 256u) : 0u;
+        if ((s[0] >> LB_FLAG_SHIFT) == 0u) {                   // nearest one not published yet: poll again
             if (++spins > SPIN_LIMIT) { if (err) atomicOr(err, 1u); st.done = true; }
             continue;
         }
-        st.excl += s0 & LB_VALUE_MASK; --p;
-        if ((s0 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
-        if (n < 1 || (s1 >> LB_FLAG_SHIFT) == 0u) continue;
-        st.excl += s1 & LB_VALUE_MASK; --p;
-        if ((s1 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
-        if (n < 2 || (s2 >> LB_FLAG_SHIFT) == 0u) continue;
-        st.excl += s2 & LB_VALUE_MASK; --p;
-        if ((s2 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
-        if (n < 3 || (s3 >> LB_FLAG_SHIFT) == 0u) continue;
-        st.excl += s3 & LB_VALUE_MASK; --p;
-        if ((s3 >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
+#pragma unroll
+        for (int k = 0; k < LB_WIDTH; k++) {
+            if (n < k || (s[k] >> LB_FLAG_SHIFT) == 0u) break;          // beyond the level / not published: next step starts here
+            st.excl += s[k] & LB_VALUE_MASK; --p;
+            if ((s[k] >> LB_FLAG_SHIFT) == 2u) { st.done = true; return; }
+        }
     }
 }
 
@@ -103,12 +106,28 @@ onesweep_pass_kernel(SortPassArgs a)
             if ((int)lane >= o) incl += t;
         }
         if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
+        // a pass whose digit is the same for every key (one bin holds all n keys: the top byte of the compressed layout's
+        // 24-bit depth key) is the identity permutation: stream the pairs through, no ranking, no look-back
+        const int ident = __syncthreads_or((n > 0u && c == n) ? 1 : 0);
         uint32_t woff = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++) if (w < (int)warp) woff += s_scan[w];
         g_excl = woff + incl - c;
         __syncthreads();
+        if (ident) {
+            for (uint32_t i = blockIdx.x * SORT_THREADS + tid; i < n; i += gridDim.x * SORT_THREADS) {
+                const uint32_t kk = a.keys_in[i];
+                if (a.keys_out) a.keys_out[i] = kk;
+                a.vals_out[i] = a.vals_in[i];
+                if (EMIT_RANGES) {
+                    const bool first = (i == 0u) || (a.keys_in[i - 1u] != kk);
+                    const bool last = (i == n - 1u) || (a.keys_in[i + 1u] != kk);
+                    if (first) atomicMin(&a.ranges[kk].x, i);
+                    if (last) atomicMin(&a.ranges[kk].y, ~(i + 1u));
+                }
+            }
+            return;
+        }
     }
 
     for (;;) {
@@ -265,7 +284,7 @@ onesweep_pass_kernel(SortPassArgs a)
             if (i < nvalid) {
                 const uint32_t kk = s_keys[i];
                 const uint32_t g = s_gbase[(kk >> shift) & 255u] + i;
-                a.keys_out[g] = kk;
+                if (a.keys_out) a.keys_out[g] = kk;           // NULL on the last tile pass: nothing downstream reads the sorted tile ids
                 a.vals_out[g] = s_vals[i];
                 if (EMIT_RANGES) {
                     // The output of the last pass is fully sorted, so equal keys are contiguous in
@@ -284,7 +303,7 @@ onesweep_pass_kernel(SortPassArgs a)
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// V2 of the pass (default): what ncu named on V1 (r01m/r01q: SM 30-37 %, short_scoreboard 28-33 % + long_scoreboard
+// V2 of the pass (WS_SORT_VARIANT=2; NOT the default -- measured, profiles/r02a_*): what ncu named on V1 (r01m/r01q: SM 30-37 %, short_scoreboard 28-33 % + long_scoreboard
 // 20-25 %, ~38 shared-memory wavefront cycles per warp-item on random digits) is attacked three ways:
 //   * TMA staging: the NEXT partition's keys and values (2 x 16 KB) are fetched by cp.async.bulk (UBLKCP) into a
 //     staging buffer while the current partition is in its look-back and write-out; the ticket of the next partition
@@ -297,6 +316,11 @@ onesweep_pass_kernel(SortPassArgs a)
 // Also: a pass whose digit is the same for every key (one histogram bin holds all n keys -- the top byte of the
 // compressed layout's 24-bit key) degenerates to a plain copy, and the last tile pass may skip the key store
 // (keys_out == NULL: the compositor only needs the values and the tile ranges).
+// RESULT (B200, profiles/r02a_sort_v{1,2}.jsonl): no faster than V1 on its own (depth pass 49.9 vs 48.9 us, 21 M-pair tile
+// pass 138.7 vs 133.6 us, 10.5 M pairs 71.2 vs 73.2 us) -- neither the load latency nor the shared-memory wavefronts were
+// the bound; the look-back walk was (see lookback_level) -- and with two frames in flight the frame rate FELL from 819
+// to 237 frames/s: 3 CTAs x 75 KB take every SM's shared memory, so no kernel of the other frame can ever share an SM
+// with a sort pass.  V1 (41 KB static) stays the default; V2 is kept as the measured TMA-staged alternative.
 struct SortSmemV2 {
     uint32_t stage_k[SORT_PART];              // TMA destination: next partition's keys ...
     uint32_t stage_v[SORT_PART];              // ... and values
@@ -545,9 +569,9 @@ static int rank_ways()
 static int sort_variant()
 {
     static int v = [] {
-        const char *e = getenv("WS_SORT_VARIANT");           // 2 = TMA-staged pass (default), 1 = the round-1 pass (kept for A/B in profiles/)
-        const int w = e ? atoi(e) : 2;
-        return (w == 1) ? 1 : 2;
+        const char *e = getenv("WS_SORT_VARIANT");           // 1 = register-staged pass (default), 2 = the TMA-staged pass (measured alternative, see above)
+        const int w = e ? atoi(e) : 1;
+        return (w == 2) ? 2 : 1;
     }();
     return v;
 }
@@ -577,7 +601,6 @@ cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t strea
         else onesweep_pass_v2_kernel<false><<<grid, SORT_THREADS, SORT_V2_SMEM, stream>>>(a);
         return cudaGetLastError();
     }
-    if (!a.keys_out) return cudaErrorInvalidValue;           // only the V2 pass can drop the key store
     const int w = rank_ways();
 #define WS_LAUNCH(R, W) onesweep_pass_kernel<R, W><<<grid, SORT_THREADS, 0, stream>>>(a)
     if (a.ranges) { if (w == 4) WS_LAUNCH(true, 4); else if (w == 2) WS_LAUNCH(true, 2); else WS_LAUNCH(true, 1); }
@@ -586,7 +609,7 @@ cudaError_t launch_sort_pass(const SortPassArgs &a, int grid, cudaStream_t strea
     return cudaGetLastError();
 }
 
-bool sort_pass_can_skip_keys() { return sort_variant() == 2; }
+bool sort_pass_can_skip_keys() { return true; }
 
 int sort_pass_blocks_per_sm()
 {

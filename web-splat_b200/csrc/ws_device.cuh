@@ -36,6 +36,12 @@ struct FrameUniforms {      // one device-resident block per renderer, rewritten
     Quant4 quant;
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t num_points, file_sh_deg, pair_capacity, _pad0;
+    // per-frame constants of stage 1 that the shaders recompute per invocation (preprocess.wgsl:270-271, :263-264, :199);
+    // divided once on the host in IEEE f32 -- the same bits a per-thread IEEE division gives
+    float inv_viewport[2];      // 1 / viewport
+    float znear, zfar;          // -proj[3][2] / proj[2][2],  -proj[3][2] / (proj[2][2] - 1)
+    float inv_scene_extend;     // 1 / scene_extend
+    float _padf[3];
 };
 
 // ---- per-frame device counters (zeroed by one memset per frame) ---------------
