@@ -496,3 +496,14 @@ def test_deferred_frame_status_and_index_validation(ws, ctx):
             r2.render(t2, pc2)
             torch.cuda.synchronize(dev)
             assert np.array_equal(t2.cpu().numpy(), img0)
+
+
+@pytest.mark.parametrize("scaling,n,W,H", [(6.0, 3000, 640, 360), (10.0, 700, 1920, 1080), (1.0, 40000, 1200, 799)])
+def test_binning_large_rectangles(ws, orc, ctx, scaling, n, W, H):
+    """bin_expand: rectangles above 32 tiles are expanded by the whole block, small ones by their owner thread, partitions
+    with more than 4096 pairs in several chunks -- the (tile, slot) pair list, ranges and image must not care
+    (gaussian_scaling blows the splats up: hundreds to thousands of tiles each, screen-filling ones included)."""
+    cloud = ws.synth.make_cloud(n, 123 + n)
+    pos, rot = ws.synth.orbit_camera(300.0)
+    r, st, d = _check_all_stages(ws, orc, ctx, cloud, pos, rot, W, H, gaussian_scaling=scaling)
+    assert st["num_pairs"] > (20 * st["num_visible"] if scaling > 1 else st["num_visible"])

@@ -15,13 +15,10 @@
 // ticket / gather / look-back round trips and the kernel ran at 8 % of the HBM roofline):
 //   COUNT   pairs per 1024-splat partition (slot load + rectangle gather, 4 per thread in flight);
 //   SCAN    one CTA: exclusive scan of the partition totals, P, overflow flag;
-//   EXPAND  load-balanced over PAIRS, not splats: every splat with at least one tile drops a
-//           marker (its index) at the block-local offset of its first pair, a prefix-max over
-//           the positions (warp shuffles, 8 positions per thread) tells every output position
-//           which splat owns it, and the thread derives (tile x, tile y) from the position with
-//           one multiply-high (magic reciprocal of the rectangle width).  Threads emit
-//           consecutive pairs straight to global memory, perfectly coalesced, however uneven
-//           the rectangles are (a screen-filling splat simply owns many consecutive positions).
+//   EXPAND  pairs are staged in shared memory at their block-local output position (scan of the
+//           per-splat counts) and leave as perfectly coalesced stores; a splat's owner thread walks
+//           its rectangle (3.5 tiles on average), rectangles above 32 tiles are walked by the whole
+//           block together, so a screen-filling splat costs no more than its share of positions.
 // The digit histogram uses plain shared-memory atomicAdd (no return value): measured at
 // 118-135 G warp-ops/s on B200 whatever the address spread, 25x a MATCH.ANY-aggregated update
 // (profiles/microbench/rank_primitives.cu).
@@ -36,8 +33,6 @@ constexpr int BIN_THREADS = 256;
 constexpr int BIN_WARPS = BIN_THREADS / 32;
 constexpr int BIN_SPT = 4;                            // splats per thread
 constexpr int BIN_PART = BIN_THREADS * BIN_SPT;       // 1024 splats per partition
-constexpr int BIN_ROUNDS = 8;                         // output positions per thread and chunk
-constexpr int BIN_CAP = BIN_THREADS * BIN_ROUNDS;     // 2048 pairs per chunk
 constexpr int BIN_NDIG = 3;
 
 struct SplatRects { uint32_t slot[BIN_SPT], xy[BIN_SPT], w[BIN_SPT], h[BIN_SPT], cnt[BIN_SPT]; };
@@ -78,7 +73,7 @@ __device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first,
 // far slab: a splat all of whose tiles were saturated by the near slab cannot change a pixel.  Only small rectangles are
 // tested (they are almost all of them); a pair emitted for a saturated tile is harmless, the compositor skips that tile.
 // Returns the keep bytes for load_rects (the expand kernel does not repeat the test, nor fetch the dropped rectangles).
-__device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRects &r)
+__device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRects &r, const uint8_t *done)
 {
     const uint32_t tiles_x = a.uniforms->tiles_x;
     uint32_t keep4 = 0u;
@@ -88,7 +83,7 @@ __device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRe
             const uint32_t x0 = r.xy[j] & 0xffffu, y0 = r.xy[j] >> 16;
             bool all = true;
             for (uint32_t yy = 0; yy < r.h[j]; yy++)
-                for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (a.tile_done[(y0 + yy) * tiles_x + x0 + xx] != 0);
+                for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (done[(y0 + yy) * tiles_x + x0 + xx] != 0);
             if (all) r.cnt[j] = 0u;
         }
         if (r.cnt[j] > 0u) keep4 |= 1u << (8 * j);
@@ -101,15 +96,27 @@ __global__ void __launch_bounds__(BIN_THREADS)
 bin_count_kernel(BinningArgs a)
 {
     __shared__ uint32_t s_red[BIN_WARPS];
+    extern __shared__ __align__(16) uint8_t s_done[];   // far slab: the per-tile "saturated" bytes (T of them, when they fit)
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
     uint32_t lo, hi;
     slab_bounds(a, V, lo, hi);
     const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
+    // The saturation test reads one byte per tile of every small rectangle: random gathers (r02a: 43 us for the far half
+    // of cfg3, long_scoreboard 10 warps per issue).  The whole map is 8 KB at 1080p, 32 KB at 4K: stage it per CTA.
+    const uint8_t *done = a.tile_done;
+    if (a.tile_done && a.done_in_smem) {
+        const uint32_t T = a.uniforms->tiles_x * a.uniforms->tiles_y;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tile_done);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_done);
+        for (uint32_t i = tid; i < (T + 15u) / 16u; i += BIN_THREADS) dst[i] = src[i];     // the allocation is padded to 16 B
+        __syncthreads();
+        done = s_done;
+    }
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         SplatRects r;
         load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r);
-        if (a.tile_done) a.keep4[part * BIN_THREADS + tid] = drop_saturated(a, r);
+        if (a.tile_done) a.keep4[part * BIN_THREADS + tid] = drop_saturated(a, r, done);
         uint32_t c = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -142,15 +149,26 @@ bin_scan_kernel(BinningArgs a)
 }
 
 // ---- (3) EXPAND ----------------------------------------------------------------------------------
+// Round 2 rewrite.  ncu on the round-1 kernel (profiles/r02a: 139 lane-instructions per emitted pair, 1168 SASS
+// instructions, the marker / prefix-max machinery executed for every output position) showed the general
+// load-balancing scheme costing 3x what the data needs: a splat touches 3.5 tiles on average, so the owner thread
+// simply walks its own rectangle.  Only rectangles above EXP_SMALL tiles (close-ups, gaussian_scaling > 1) are expanded
+// cooperatively by the whole block, one 256-wide stride per rectangle.  Pairs are staged in shared memory at their
+// block-local output position (scan of the per-splat counts), so the stores to global memory stay perfectly
+// coalesced and the output order -- splat (depth order), then row-major tile -- is exactly that of round 1.
+constexpr int EXP_CAP = 4096;                         // staged pairs per chunk (2 x 16 KB)
+constexpr uint32_t EXP_SMALL = 32;                    // rectangles up to this many tiles are walked by their owner thread
+constexpr int EXP_BIG = 512;                          // cooperative list entries per partition (beyond: owner thread walks)
+
 __global__ void __launch_bounds__(BIN_THREADS, 4)
 bin_expand_kernel(BinningArgs a)
 {
-    __shared__ uint32_t s_owner[BIN_CAP];             // marker = owner index + 1 at the owner's first position
-    __shared__ uint4 s_info[BIN_PART];                // per splat: {first pair (block-local), x0 | y0<<16, slot, width}
-    __shared__ uint32_t s_magic[BIN_PART];            // ceil(2^32 / width)
+    __shared__ uint32_t s_tile[EXP_CAP];
+    __shared__ uint32_t s_slot[EXP_CAP];
+    __shared__ uint4 s_big[EXP_BIG];                  // {first pair (block-local), x0 | y0<<16, slot, w | h<<16}
     __shared__ uint32_t s_hist[BIN_NDIG][256];
     __shared__ uint32_t s_scan[BIN_WARPS];
-    __shared__ uint32_t s_wcarry[BIN_WARPS];
+    __shared__ uint32_t s_nbig;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t V = a.counters->num_visible;
@@ -163,6 +181,7 @@ bin_expand_kernel(BinningArgs a)
     const int ndig = (ntiles > 65536u) ? 3 : ((ntiles > 256u) ? 2 : 1);
 
     for (unsigned i = tid; i < (unsigned)(BIN_NDIG * 256); i += BIN_THREADS) (&s_hist[0][0])[i] = 0u;
+    if (tid == 0) s_nbig = 0u;
     __syncthreads();
 
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
@@ -171,7 +190,7 @@ bin_expand_kernel(BinningArgs a)
         const uint32_t base = __ldg(a.part_bases + part);
         if (base >= cap) continue;                        // beyond the pair capacity (overflow is already flagged): nothing of this partition is stored
         const uint32_t mine = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
-        // block scan of the per-thread totals
+        // block scan of the per-thread totals -> block-local position of every splat's first pair
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -191,73 +210,61 @@ bin_expand_kernel(BinningArgs a)
         excl[0] = incl + woff - mine;
 #pragma unroll
         for (int j = 1; j < BIN_SPT; j++) excl[j] = excl[j - 1] + r.cnt[j - 1];
+        // large rectangles go to the cooperative list (any order: every pair's position is fixed by excl)
+        bool own[BIN_SPT];
 #pragma unroll
         for (int j = 0; j < BIN_SPT; j++) {
-            s_info[tid * BIN_SPT + j] = make_uint4(excl[j], r.xy[j], r.slot[j], r.w[j]);
-            s_magic[tid * BIN_SPT + j] = (r.w[j] > 1u) ? __float2uint_ru(__fdiv_ru(4294967296.f, (float)r.w[j])) : 0u;
-            // m >= 2^32/w with m*w - 2^32 <= w + 512: floor(t/w) == umulhi(t, m) for every t < 2^20, w <= 1024 (viewport <= 16384)
+            own[j] = r.cnt[j] > 0u;
+            if (r.cnt[j] > EXP_SMALL) {
+                const uint32_t e = atomicAdd(&s_nbig, 1u);
+                if (e < (uint32_t)EXP_BIG) { s_big[e] = make_uint4(excl[j], r.xy[j], r.slot[j], r.w[j] | (r.h[j] << 16)); own[j] = false; }
+            }
         }
+        __syncthreads();
+        const uint32_t nbig = s_nbig < (uint32_t)EXP_BIG ? s_nbig : (uint32_t)EXP_BIG;
 
-        for (uint32_t c0 = 0; c0 < total; c0 += BIN_CAP) {
-            const uint32_t m = (total - c0 < (uint32_t)BIN_CAP) ? total - c0 : (uint32_t)BIN_CAP;
-            const uint32_t rounds = (m + BIN_THREADS - 1u) / BIN_THREADS;       // 32-position rounds per warp
-            const uint32_t span = rounds * 32u;                                 // consecutive positions owned by a warp
-            // 1. clear, 2. markers
-            for (uint32_t q = tid; q < m; q += BIN_THREADS) s_owner[q] = 0u;
-            __syncthreads();
+        for (uint32_t c0 = 0; c0 < total; c0 += EXP_CAP) {
+            const uint32_t m = (total - c0 < (uint32_t)EXP_CAP) ? total - c0 : (uint32_t)EXP_CAP;
+            // 1. owner threads walk their (small) rectangles, row-major
 #pragma unroll
             for (int j = 0; j < BIN_SPT; j++) {
-                if (r.cnt[j] > 0u) {
-                    if (excl[j] >= c0 && excl[j] < c0 + m) s_owner[excl[j] - c0] = tid * BIN_SPT + j + 1u;
-                    else if (excl[j] < c0 && excl[j] + r.cnt[j] > c0) s_owner[0] = tid * BIN_SPT + j + 1u;   // continues from the previous chunk
+                if (own[j] && excl[j] < c0 + m && excl[j] + r.cnt[j] > c0) {
+                    const uint32_t x0 = r.xy[j] & 0xffffu, y0 = r.xy[j] >> 16;
+                    uint32_t o = excl[j] - c0;                               // may wrap below 0 for a rectangle continuing from the previous chunk: tested per pair
+                    uint32_t row = y0 * tiles_x + x0;
+                    for (uint32_t yy = 0; yy < r.h[j]; yy++, row += tiles_x)
+                        for (uint32_t xx = 0; xx < r.w[j]; xx++, o++)
+                            if (o < m) { s_tile[o] = row + xx; s_slot[o] = r.slot[j]; }
+                }
+            }
+            // 2. the block walks the large rectangles together
+            for (uint32_t b = 0; b < nbig; b++) {
+                const uint4 inf = s_big[b];
+                const uint32_t w = inf.w & 0xffffu, cnt = w * (inf.w >> 16);
+                if (inf.x >= c0 + m || inf.x + cnt <= c0) continue;          // block-uniform
+                const uint32_t q0 = (inf.x < c0) ? c0 - inf.x : 0u;          // first pair of the rectangle inside this chunk
+                const uint32_t q1 = (inf.x + cnt > c0 + m) ? c0 + m - inf.x : cnt;
+                const uint32_t origin = (inf.y >> 16) * tiles_x + (inf.y & 0xffffu);
+                for (uint32_t q = q0 + tid; q < q1; q += BIN_THREADS) {
+                    const uint32_t ty = q / w, tx = q - ty * w;
+                    const uint32_t o = inf.x + q - c0;
+                    s_tile[o] = origin + ty * tiles_x + tx; s_slot[o] = inf.z;
                 }
             }
             __syncthreads();
-            // 3. prefix-max of the markers over this warp's span
-            uint32_t own[BIN_ROUNDS];
-            uint32_t carry = 0;
-#pragma unroll
-            for (int k = 0; k < BIN_ROUNDS; k++) {
-                own[k] = 0u;
-                if ((uint32_t)k < rounds) {
-                    const uint32_t q = warp * span + (uint32_t)k * 32u + lane;
-                    uint32_t v = (q < m) ? s_owner[q] : 0u;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-                        if ((int)lane >= o) v = v > t ? v : t;
-                    }
-                    v = v > carry ? v : carry;
-                    carry = __shfl_sync(0xffffffffu, v, 31);
-                    own[k] = v;
-                }
-            }
-            if (lane == 0) s_wcarry[warp] = carry;
-            __syncthreads();
-            uint32_t prev = 0;
-#pragma unroll
-            for (int k = 0; k < BIN_WARPS; k++) if (k < (int)warp) { const uint32_t c = s_wcarry[k]; prev = prev > c ? prev : c; }
-            // 4. emit: position -> (tile, slot), coalesced, plus the tile-id digit histogram
-#pragma unroll
-            for (int k = 0; k < BIN_ROUNDS; k++) {
-                if ((uint32_t)k < rounds) {
-                    const uint32_t q = warp * span + (uint32_t)k * 32u + lane;
-                    const uint64_t g = (uint64_t)base + c0 + q;
-                    if (q < m && g < cap) {
-                        const uint32_t o = (own[k] > prev ? own[k] : prev) - 1u;
-                        const uint4 inf = s_info[o];
-                        const uint32_t t = c0 + q - inf.x;
-                        const uint32_t ty = (inf.w > 1u) ? __umulhi(t, s_magic[o]) : t;
-                        const uint32_t tx = t - ty * inf.w;
-                        const uint32_t tile = ((inf.y >> 16) + ty) * tiles_x + (inf.y & 0xffffu) + tx;
-                        a.pair_tiles[g] = tile;
-                        a.pair_slots[g] = inf.z;
-                        for (int d = 0; d < ndig; d++) atomicAdd(&s_hist[d][(tile >> (8 * d)) & 255u], 1u);
-                    }
+            // 3. coalesced copy-out + tile-id digit histograms
+            for (uint32_t i = tid; i < m; i += BIN_THREADS) {
+                const uint64_t g = (uint64_t)base + c0 + i;
+                if (g < cap) {
+                    const uint32_t tile = s_tile[i];
+                    a.pair_tiles[g] = tile;
+                    a.pair_slots[g] = s_slot[i];
+                    for (int d = 0; d < ndig; d++) atomicAdd(&s_hist[d][(tile >> (8 * d)) & 255u], 1u);
                 }
             }
             __syncthreads();
         }
+        if (tid == 0) s_nbig = 0u;
         __syncthreads();
     }
 
@@ -271,7 +278,11 @@ bin_expand_kernel(BinningArgs a)
 
 cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand, cudaStream_t stream)
 {
-    bin_count_kernel<<<grid_count, BIN_THREADS, 0, stream>>>(a);
+    // far slab: the tile_done map travels in dynamic shared memory when it fits under the 48 KB default limit
+    BinningArgs ac = a;
+    const size_t done_bytes = (a.tile_done && a.num_tiles_hint && a.num_tiles_hint <= 40000u) ? ((size_t)a.num_tiles_hint + 15u) / 16u * 16u : 0u;
+    ac.done_in_smem = done_bytes ? 1u : 0u;
+    bin_count_kernel<<<grid_count, BIN_THREADS, done_bytes, stream>>>(ac);
     bin_scan_kernel<<<1, 1024, 0, stream>>>(a);
     bin_expand_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
     return cudaGetLastError();

@@ -690,8 +690,12 @@ struct ShardState {
     uint8_t *peer_frame[8][2] = {};            // every rank's two assembled-frame buffers (frame parity; only the root's are written)
     uint8_t *d_shard_frame[2] = {nullptr, nullptr}; size_t shard_frame_bytes = 0;
     ShardMailbox *d_mail = nullptr, *peer_mail[8] = {};   // rows / barrier / band flags written by the peers
-    uint32_t epoch = 0;
+    uint32_t epoch = 0;                        // host mirror of *d_epoch
+    uint32_t *d_epoch = nullptr;               // frame number in device memory (advanced by the frame itself: graph replay)
     uint32_t *pending_signal = nullptr;        // set for the next band composite only
+    // CUDA graphs of the single-call sharded frame (ws_renderer_shard_frame_to_root), one per frame-buffer parity
+    cudaGraphExec_t frame_exec[2] = {nullptr, nullptr};
+    struct { uint64_t pc_gen, buf_gen; uint32_t root, gated, bands[9]; float clear[4]; bool split; } frame_key[2] = {};
     bool opened[8] = {};
     bool imported = false;
     int phase = 0;
@@ -915,7 +919,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         cudaFree(r->d_ranges); r->d_ranges = nullptr;
         CU(cudaMalloc(&r->d_ranges, (size_t)(tiles ? tiles : 1) * 8 * 2));      // [tiles] near / only, [tiles] far slab
         cudaFree(r->d_tile_done); r->d_tile_done = nullptr;
-        CU(cudaMalloc(&r->d_tile_done, tiles ? tiles : 1));
+        CU(cudaMalloc(&r->d_tile_done, (size_t)(tiles ? tiles : 1) + 16));     // + 16: bin_count stages it with 128-bit loads
         r->tiles_cap = tiles;
         r->buf_generation = next_generation();
     }
@@ -1065,6 +1069,7 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
             a.part_counts = r->d_scan_bin; a.part_bases = r->d_bin_bases; a.hist = r->d_hist_tile + half * 4 * 256;
             a.slab = slab; a.tile_done = (slab == 2u) ? r->d_tile_done : nullptr; a.pair_cap = cap; a.num_pairs_out = num_pairs;
             a.keep4 = r->d_keep4;
+            a.num_tiles_hint = r->h_uniforms.tiles_x * r->h_uniforms.tiles_y; a.done_in_smem = 0;
             CU(launch_binning(a, r->ctx->sm_count * 8, r->grid_bin, stream));
         }
         if (r->timing) CU(cudaEventRecord(r->ev[ev_bin], stream));
@@ -1193,7 +1198,8 @@ static void free_shard(ws_renderer *r)
             s.opened[p] = false;
         }
     }
-    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame[0]); cudaFree(s.d_shard_frame[1]); cudaFree(s.d_mail);
+    for (int i = 0; i < 2; i++) if (s.frame_exec[i]) cudaGraphExecDestroy(s.frame_exec[i]);
+    cudaFree(s.l_splats); cudaFree(s.l_keys); cudaFree(s.l_vals); cudaFree(s.l_rects); cudaFree(s.d_route); cudaFree(s.d_shard_frame[0]); cudaFree(s.d_shard_frame[1]); cudaFree(s.d_mail); cudaFree(s.d_epoch);
     s = ShardState();
 }
 
@@ -1224,6 +1230,8 @@ extern "C" ws_status ws_renderer_shard_configure(ws_renderer *r, uint32_t rank, 
     CU(cudaMalloc(&s.d_shard_frame[0], s.shard_frame_bytes)); CU(cudaMalloc(&s.d_shard_frame[1], s.shard_frame_bytes));
     CU(cudaMalloc(&s.d_mail, sizeof(ShardMailbox)));
     CU(cudaMemset(s.d_mail, 0, sizeof(ShardMailbox)));
+    CU(cudaMalloc(&s.d_epoch, 4));
+    CU(cudaMemset(s.d_epoch, 0, 4));
     s.peer_splats[rank] = r->d_splats; s.peer_keys[rank] = r->d_keys[0]; s.peer_rects[rank] = r->d_rects;
     s.peer_frame[rank][0] = s.d_shard_frame[0]; s.peer_frame[rank][1] = s.d_shard_frame[1];
     s.peer_mail[rank] = s.d_mail;
@@ -1314,7 +1322,7 @@ static void fill_route_args(ws_renderer *r, RouteArgs &a)
     for (int p = 0; p < 8; p++) { a.peer_splats[p] = s.peer_splats[p]; a.peer_keys[p] = s.peer_keys[p]; a.peer_rects[p] = s.peer_rects[p]; }
     a.recv_cap = s.recv_cap; a.err = &r->d_counters->error_flags;
     for (int p = 0; p < 8; p++) a.peer_mail[p] = nullptr;          // NCCL mode unless the caller fills these in
-    a.epoch = 0; a.done_counter = &r->d_counters->scatter_done;
+    a.epoch_ptr = s.d_epoch; a.done_counter = &r->d_counters->scatter_done;
 }
 
 extern "C" ws_status ws_renderer_shard_begin(ws_renderer *r, ws_pointcloud *pc, const ws_splatting_args *args,
@@ -1388,6 +1396,9 @@ extern "C" ws_status ws_renderer_shard_finish(ws_renderer *r, const uint32_t *ma
 
 static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch, const double clear[4],
                              void *cuda_stream, uint32_t tile_y0, uint32_t tile_rows);
+static ws_status enqueue_composite(ws_renderer *r, void *dst, size_t row_pitch, const double clear[4], cudaStream_t stream,
+                                   uint32_t tile_y0, uint32_t tile_rows);
+static ws_status enqueue_status_copy(ws_renderer *r, cudaStream_t stream);
 
 // The whole sharded frame in ONE call and with NO host-side collective: the count rows, the barrier
 // after the exchange and the "band has landed" signal are epoch flags that the kernels themselves
@@ -1412,43 +1423,81 @@ extern "C" ws_status ws_renderer_shard_frame_to_root(ws_renderer *r, ws_pointclo
     // rank's share of the cloud is large enough to pay for the extra launches (2 GPUs at cfg3: yes; 8 GPUs: no)
     st = decide_split(r, (uint64_t)s.recv_cap / s.world, s.width, s.height);
     if (st != WS_OK) return st;
-    st = begin_frame(r, pc, args, s.recv_cap, stream);
+    st = begin_frame(r, pc, args, s.recv_cap, stream, /*with_clears=*/false);      // uniforms (an ordinary async copy in front of the frame)
     if (st != WS_OK) return st;
-    s.epoch += 1;
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_START], stream));
-    {   // stage 1 on the local shard
-        PreprocessArgs a;
-        a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
-        a.uniforms = r->d_uniforms;
-        a.splats = s.l_splats; a.depth_keys = s.l_keys; a.slot_vals = s.l_vals; a.rects = s.l_rects;
-        a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
-        a.hist = s.hist_dummy; a.counters = r->d_counters;
-        CU(cudaMemsetAsync(s.hist_dummy, 0, 4 * 256 * 4, stream));
-        CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, stream));
-    }
-    RouteArgs ra; fill_route_args(r, ra);
-    for (uint32_t p = 0; p < s.world; p++) ra.peer_mail[p] = s.peer_mail[p];
-    ra.epoch = s.epoch;
-    CU(launch_route_count(ra, r->ctx->sm_count * 8, stream));          // counts + scan; the row goes to every rank's mailbox
-    CU(launch_route_scatter(ra, r->ctx->sm_count * 8, stream));        // waits for all rows, stores the splats into the owners' buffers
-    CU(launch_shard_finish_peer(ra, r->d_vals[0], r->d_keys[0], r->d_hist_depth, r->depth_passes, r->d_counters,
-                                r->ctx->sm_count * 4, stream));        // waits for every rank's exchange flag
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], stream));
-    st = enqueue_stage2(r, stream);
-    if (st != WS_OK) return st;
-    r->prepared = true; r->last_stream = stream; r->last_n = pc->n;
-    // stage 3: pixels go straight into the root's frame; the last CTA raises this rank's band flag there
-    const size_t pitch = s.shard_frame_bytes / s.height;
-    const uint32_t first = s.band_y0[s.rank] * TILE;
     const uint32_t rows = s.band_y0[s.rank + 1] - s.band_y0[s.rank];
-    if (rows > 0 && first < s.height) {
+    if (rows == 0 || s.band_y0[s.rank] * TILE >= s.height) return fail(WS_ERR_UNSUPPORTED, "a rank without tile rows (more ranks than tile rows) is not supported");
+    const uint32_t par = (s.epoch + 1u) & 1u;           // parity of the frame buffer this frame fills (host mirror of the device epoch:
+                                                        // committed below, once the frame -- whose first kernel advances the device word -- is enqueued)
+
+    // everything of the frame that does not depend on the frame's content: clears, epoch, stage 1, routing + exchange,
+    // stage 2, the band compositor (pixels into the root's frame of this parity), the root's wait for all bands
+    auto body = [&](cudaStream_t q) -> ws_status {
+        CU(cudaMemsetAsync(r->d_scratch, 0, r->scratch_bytes, q));
+        CU(cudaMemsetAsync(r->d_ranges, 0xff, (size_t)r->tiles_cap * 8 * (r->frame_split ? 2 : 1), q));
+        CU(cudaMemsetAsync(s.hist_dummy, 0, 4 * 256 * 4, q));
+        CU(launch_epoch_advance(s.d_epoch, q));
+        if (r->timing) CU(cudaEventRecord(r->ev[EV_START], q));
+        {   // stage 1 on the local shard
+            PreprocessArgs a;
+            a.gaussians = pc->d_gaussians; a.xyz = pc->d_xyz; a.sh_coefs = pc->d_sh; a.covars = pc->d_covars;
+            a.uniforms = r->d_uniforms;
+            a.splats = s.l_splats; a.depth_keys = s.l_keys; a.slot_vals = s.l_vals; a.rects = s.l_rects;
+            a.part_counts = r->d_scan_pre; a.part_bases = r->d_part_bases;
+            a.hist = s.hist_dummy; a.counters = r->d_counters;
+            CU(launch_preprocess(a, r->compressed, r->ctx->sm_count * 8, r->grid_pre, q));
+        }
+        RouteArgs ra; fill_route_args(r, ra);
+        for (uint32_t p = 0; p < s.world; p++) ra.peer_mail[p] = s.peer_mail[p];
+        CU(launch_route_count(ra, r->ctx->sm_count * 8, q));          // counts + scan; the row goes to every rank's mailbox
+        CU(launch_route_scatter(ra, r->ctx->sm_count * 8, q));        // waits for all rows, stores the splats into the owners' buffers
+        CU(launch_shard_finish_peer(ra, r->d_vals[0], r->d_keys[0], r->d_hist_depth, r->depth_passes, r->d_counters,
+                                    r->ctx->sm_count * 4, q));        // waits for every rank's exchange flag
+        if (r->timing) CU(cudaEventRecord(r->ev[EV_PRE], q));
+        ws_status bs = enqueue_stage2(r, q);
+        if (bs != WS_OK) return bs;
+        // stage 3: pixels go straight into the root's frame; the last CTA raises this rank's band flag there
+        const size_t pitch = s.shard_frame_bytes / s.height;
         s.pending_signal = &s.peer_mail[root]->flag_band[s.rank];
-        st = render_rows(r, pc, s.peer_frame[root][s.epoch & 1u] + (size_t)first * pitch, pitch, clear, cuda_stream, s.band_y0[s.rank], rows);
-        if (st != WS_OK) return st;
+        bs = enqueue_composite(r, s.peer_frame[root][par] + (size_t)(s.band_y0[s.rank] * TILE) * pitch, pitch, clear, q, s.band_y0[s.rank], rows);
+        if (bs != WS_OK) return bs;
+        if (s.rank == root) CU(launch_wait_bands(s.d_mail, s.world, s.d_epoch, &r->d_counters->error_flags, q));
+        return WS_OK;
+    };
+
+    if (r->use_graphs && !r->timing) {
+        // One CUDA graph per frame-buffer parity: ~25 launches + 3 clears become one launch (host: ~200 -> ~60 us per
+        // frame and rank; device: no launch gaps between the latency-bound kernels of a 1/8 share of the frame).
+        auto &k = s.frame_key[par];
+        bool same = s.frame_exec[par] && k.pc_gen == pc->generation && k.buf_gen == r->buf_generation && k.root == root &&
+                    k.gated == s.gated && k.split == r->frame_split;
+        for (int i = 0; i < 9 && same; i++) same = k.bands[i] == s.band_y0[i];
+        for (int i = 0; i < 4 && same; i++) same = k.clear[i] == (clear ? (float)clear[i] : 0.f);
+        if (!same) {
+            if (s.frame_exec[par]) { cudaGraphExecDestroy(s.frame_exec[par]); s.frame_exec[par] = nullptr; }
+            if (!r->cap_stream) CU(cudaStreamCreateWithFlags(&r->cap_stream, cudaStreamNonBlocking));
+            CU(cudaStreamBeginCapture(r->cap_stream, cudaStreamCaptureModeThreadLocal));
+            st = body(r->cap_stream);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(r->cap_stream, &g);
+            if (st != WS_OK) { if (g) cudaGraphDestroy(g); return st; }
+            if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture (sharded frame)");
+            e = cudaGraphInstantiate(&s.frame_exec[par], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { s.frame_exec[par] = nullptr; return fail_cuda(e, "cudaGraphInstantiate (sharded frame)"); }
+            k.pc_gen = pc->generation; k.buf_gen = r->buf_generation; k.root = root; k.gated = s.gated; k.split = r->frame_split;
+            for (int i = 0; i < 9; i++) k.bands[i] = s.band_y0[i];
+            for (int i = 0; i < 4; i++) k.clear[i] = clear ? (float)clear[i] : 0.f;
+        }
+        CU(cudaGraphLaunch(s.frame_exec[par], stream));
     } else {
-        return fail(WS_ERR_UNSUPPORTED, "a rank without tile rows (more ranks than tile rows) is not supported");
+        st = body(stream);
+        if (st != WS_OK) return st;
     }
-    if (s.rank == root) CU(launch_wait_bands(s.d_mail, s.world, s.epoch, &r->d_counters->error_flags, stream));
+    s.epoch += 1;
+    st = enqueue_status_copy(r, stream);
+    if (st != WS_OK) return st;
+    r->prepared = true; r->rendered = true; r->last_stream = stream; r->last_n = pc->n;
     return WS_OK;
 }
 
@@ -1511,6 +1560,39 @@ extern "C" ws_status ws_renderer_shard_download(ws_renderer *r, void *dst_host, 
     return WS_OK;
 }
 
+// stage 3 launch only (capturable): the compositor over tile rows [tile_y0, tile_y0 + tile_rows) into dst
+static ws_status enqueue_composite(ws_renderer *r, void *dst, size_t row_pitch, const double clear[4], cudaStream_t stream,
+                                   uint32_t tile_y0, uint32_t tile_rows)
+{
+    const FrameUniforms &U = r->h_uniforms;
+    CompositeArgs a;
+    memset(&a, 0, sizeof a);
+    a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
+    if (r->frame_split) {               // the far slab's list on top of the state the near slab left
+        a.pair_slots = r->d_pslots[r->tile_out_far]; a.ranges = r->d_ranges + r->tiles_cap;
+        a.mode = 2; a.state = r->d_state; a.tile_done = r->d_tile_done;
+    }
+    a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
+    a.tile_y0 = tile_y0;
+    a.signal_flag = r->shard.pending_signal; a.signal_epoch = r->shard.d_epoch; a.done_counter = &r->d_counters->composite_done;
+    r->shard.pending_signal = nullptr;
+    for (int i = 0; i < 4; i++) a.clear[i] = clear ? (float)clear[i] : 0.f;
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND0], stream));
+    if (tile_rows) CU(launch_composite(a, U.tiles_x, tile_rows, stream));
+    if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND1], stream));
+    return WS_OK;
+}
+
+// this frame's {V, P, pair_overflow, error_flags} -> a pinned slot; checked (never waited for) by later calls
+static ws_status enqueue_status_copy(ws_renderer *r, cudaStream_t stream)
+{
+    const int slot = r->flag_next; r->flag_next = (slot + 1) % ws_renderer::FLAG_SLOTS;
+    CU(cudaMemcpyAsync(r->h_flags + 4 * slot, r->d_counters, 16, cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(r->ev_flags[slot], stream));
+    r->flags_pending[slot] = true;
+    return WS_OK;
+}
+
 static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_t row_pitch, const double clear[4],
                              void *cuda_stream, uint32_t tile_y0, uint32_t tile_rows)
 {
@@ -1523,27 +1605,10 @@ static ws_status render_rows(ws_renderer *r, ws_pointcloud *pc, void *dst, size_
     if (((uintptr_t)dst % bpp) != 0) return fail(WS_ERR_INVALID_ARGUMENT, "dst is not aligned to the pixel size");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(cudaSetDevice(r->ctx->device));
-    CompositeArgs a;
-    memset(&a, 0, sizeof a);
-    a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
-    if (r->frame_split) {               // the far slab's list on top of the state the near slab left
-        a.pair_slots = r->d_pslots[r->tile_out_far]; a.ranges = r->d_ranges + r->tiles_cap;
-        a.mode = 2; a.state = r->d_state; a.tile_done = r->d_tile_done;
-    }
-    a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
-    a.tile_y0 = tile_y0;
-    a.signal_flag = r->shard.pending_signal; a.signal_epoch = r->shard.epoch; a.done_counter = &r->d_counters->composite_done;
-    r->shard.pending_signal = nullptr;
-    for (int i = 0; i < 4; i++) a.clear[i] = clear ? (float)clear[i] : 0.f;
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND0], stream));
-    if (tile_rows) CU(launch_composite(a, U.tiles_x, tile_rows, stream));
-    if (r->timing) CU(cudaEventRecord(r->ev[EV_BLEND1], stream));
-    {   // this frame's {V, P, pair_overflow, error_flags} -> a pinned slot; checked (never waited for) by later calls
-        const int slot = r->flag_next; r->flag_next = (slot + 1) % ws_renderer::FLAG_SLOTS;
-        CU(cudaMemcpyAsync(r->h_flags + 4 * slot, r->d_counters, 16, cudaMemcpyDeviceToHost, stream));
-        CU(cudaEventRecord(r->ev_flags[slot], stream));
-        r->flags_pending[slot] = true;
-    }
+    ws_status st = enqueue_composite(r, dst, row_pitch, clear, stream, tile_y0, tile_rows);
+    if (st != WS_OK) return st;
+    st = enqueue_status_copy(r, stream);
+    if (st != WS_OK) return st;
     r->rendered = true;
     r->last_stream = stream;
     return WS_OK;

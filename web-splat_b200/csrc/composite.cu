@@ -225,7 +225,7 @@ composite_kernel(CompositeArgs a)
         __syncthreads();
         if (tid == 0) {
             const uint32_t prev = atomicAdd(a.done_counter, 1u);
-            if (prev == gridDim.x * gridDim.y - 1u) { __threadfence_system(); st_release_sys(a.signal_flag, a.signal_epoch); }
+            if (prev == gridDim.x * gridDim.y - 1u) { __threadfence_system(); st_release_sys(a.signal_flag, *a.signal_epoch); }
         }
     }
 }

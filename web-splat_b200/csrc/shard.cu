@@ -117,14 +117,15 @@ route_scan_kernel(RouteArgs a)
     }
     if (a.peer_mail[a.rank]) {
         // publish this rank's row into EVERY rank's mailbox, then raise the row flag (release, system scope)
-        const uint32_t par = a.epoch & 1u;
+        const uint32_t epoch = *a.epoch_ptr;          // frame number in device memory: the frame replays as a CUDA graph
+        const uint32_t par = epoch & 1u;
         if (tid < a.world * a.world) {
             const uint32_t p = tid / a.world, d = tid - p * a.world;
             a.peer_mail[p]->matrix[par][a.rank * a.world + d] = s_tot[d];
         }
         __threadfence_system();
         __syncthreads();
-        if (tid < a.world) st_release_sys(&a.peer_mail[tid]->flag_rows[a.rank], a.epoch);
+        if (tid < a.world) st_release_sys(&a.peer_mail[tid]->flag_rows[a.rank], epoch);
     }
 }
 
@@ -141,10 +142,11 @@ route_scatter_kernel(RouteArgs a)
     const uint32_t V = a.counters->num_visible;
     const uint32_t nparts = (V + RT_PART - 1u) / RT_PART;
     const uint32_t *matrix = a.matrix;
+    const uint32_t epoch = a.peer_mail[a.rank] ? *a.epoch_ptr : 0u;
     if (a.peer_mail[a.rank]) {                    // mailbox mode: wait until every rank's count row of this frame has arrived
-        if (!a.gated && tid < a.world) wait_epoch(&a.peer_mail[a.rank]->flag_rows[tid], a.epoch, a.err);
+        if (!a.gated && tid < a.world) wait_epoch(&a.peer_mail[a.rank]->flag_rows[tid], epoch, a.err);
         __syncthreads();
-        matrix = a.peer_mail[a.rank]->matrix[a.epoch & 1u];
+        matrix = a.peer_mail[a.rank]->matrix[epoch & 1u];
     }
     if (tid < a.world) {                          // where this rank's records start in each destination
         uint32_t off = 0;
@@ -230,7 +232,7 @@ route_scatter_kernel(RouteArgs a)
             const uint32_t prev = atomicAdd(a.done_counter, 1u);
             if (prev == gridDim.x - 1u) {
                 __threadfence_system();
-                for (uint32_t p = 0; p < a.world; p++) st_release_sys(&a.peer_mail[p]->flag_xchg[a.rank], a.epoch);
+                for (uint32_t p = 0; p < a.world; p++) st_release_sys(&a.peer_mail[p]->flag_xchg[a.rank], epoch);
             }
         }
     }
@@ -263,9 +265,10 @@ shard_finish_peer_kernel(RouteArgs a, uint32_t *vals, const uint32_t *__restrict
     const unsigned tid = threadIdx.x;
     for (unsigned i = tid; i < 4u * 256u; i += 256u) s_hist[i] = 0u;
     const ShardMailbox *mail = a.peer_mail[a.rank];
-    if (!a.gated && tid < a.world) wait_epoch(&mail->flag_xchg[tid], a.epoch, a.err);
+    const uint32_t epoch = *a.epoch_ptr;
+    if (!a.gated && tid < a.world) wait_epoch(&mail->flag_xchg[tid], epoch, a.err);
     __syncthreads();
-    const uint32_t *matrix = mail->matrix[a.epoch & 1u];
+    const uint32_t *matrix = mail->matrix[epoch & 1u];
     uint32_t v = 0;
     for (uint32_t s = 0; s < a.world; s++) v += matrix[s * a.world + a.rank];
     if (v > a.recv_cap) { v = a.recv_cap; if (blockIdx.x == 0 && tid == 0) atomicOr(a.err, 2u); }
@@ -280,18 +283,22 @@ shard_finish_peer_kernel(RouteArgs a, uint32_t *vals, const uint32_t *__restrict
 }
 
 // root only: the assembled frame is complete once every rank's band flag has reached the epoch
-__global__ void wait_bands_kernel(const ShardMailbox *mail, uint32_t world, uint32_t epoch, uint32_t *err)
+__global__ void wait_bands_kernel(const ShardMailbox *mail, uint32_t world, const uint32_t *epoch_ptr, uint32_t *err)
 {
-    if (threadIdx.x < world) wait_epoch(&mail->flag_band[threadIdx.x], epoch, err);
+    if (threadIdx.x < world) wait_epoch(&mail->flag_band[threadIdx.x], *epoch_ptr, err);
 }
+
+// frame number in device memory, advanced by the frame itself: nothing in a sharded frame's launch parameters changes
+// from frame to frame (apart from the frame-buffer parity: two graphs), so the whole frame replays as a CUDA graph
+__global__ void epoch_advance_kernel(uint32_t *epoch) { *epoch += 1u; }
 
 // Gate: ONE warp spins on a set of epoch flags; the kernel behind it in the stream starts once all have arrived.
 // Used instead of the in-kernel waits when several sharded frames are in flight on one GPU: a grid-wide spin
 // could fill every SM of this GPU while the peer it waits for is itself blocked behind this GPU's other frame
 // (a cross-GPU resource cycle); a one-warp gate cannot starve anything.
-__global__ void gate_kernel(const uint32_t *flags, uint32_t world, uint32_t epoch, uint32_t *err)
+__global__ void gate_kernel(const uint32_t *flags, uint32_t world, const uint32_t *epoch_ptr, uint32_t *err)
 {
-    if (threadIdx.x < world) wait_epoch(flags + threadIdx.x, epoch, err);
+    if (threadIdx.x < world) wait_epoch(flags + threadIdx.x, *epoch_ptr, err);
 }
 
 }  // namespace
@@ -300,14 +307,20 @@ cudaError_t launch_shard_finish_peer(const RouteArgs &a, uint32_t *vals, const u
                                      FrameCounters *counters, int grid, cudaStream_t stream)
 {
     // NOTE: counters->num_visible is rewritten by block 0 while other blocks of this kernel never read it
-    if (a.gated) gate_kernel<<<1, 32, 0, stream>>>(a.peer_mail[a.rank]->flag_xchg, a.world, a.epoch, a.err);
+    if (a.gated) gate_kernel<<<1, 32, 0, stream>>>(a.peer_mail[a.rank]->flag_xchg, a.world, a.epoch_ptr, a.err);
     shard_finish_peer_kernel<<<grid, 256, 0, stream>>>(a, vals, keys, hist, passes, counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_wait_bands(const ShardMailbox *mail, uint32_t world, uint32_t epoch, uint32_t *err, cudaStream_t stream)
+cudaError_t launch_wait_bands(const ShardMailbox *mail, uint32_t world, const uint32_t *epoch_ptr, uint32_t *err, cudaStream_t stream)
 {
-    wait_bands_kernel<<<1, 32, 0, stream>>>(mail, world, epoch, err);
+    wait_bands_kernel<<<1, 32, 0, stream>>>(mail, world, epoch_ptr, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_epoch_advance(uint32_t *epoch, cudaStream_t stream)
+{
+    epoch_advance_kernel<<<1, 1, 0, stream>>>(epoch);
     return cudaGetLastError();
 }
 
@@ -320,7 +333,7 @@ cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream
 
 cudaError_t launch_route_scatter(const RouteArgs &a, int grid, cudaStream_t stream)
 {
-    if (a.gated && a.peer_mail[a.rank]) gate_kernel<<<1, 32, 0, stream>>>(a.peer_mail[a.rank]->flag_rows, a.world, a.epoch, a.err);
+    if (a.gated && a.peer_mail[a.rank]) gate_kernel<<<1, 32, 0, stream>>>(a.peer_mail[a.rank]->flag_rows, a.world, a.epoch_ptr, a.err);
     route_scatter_kernel<<<grid, RT_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }

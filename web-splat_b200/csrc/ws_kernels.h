@@ -71,6 +71,8 @@ struct BinningArgs {
     uint32_t *keep4;              // slab 2: ceil(V/2/4) words, one byte per splat: count kernel -> expand kernel
     uint32_t pair_cap;            // capacity of pair_tiles / pair_slots for this launch
     uint32_t *num_pairs_out;      // device counter that receives the number of pairs of this launch
+    uint32_t num_tiles_hint;      // host-known number of tiles (sizes the shared-memory copy of tile_done); 0 = unknown
+    uint32_t done_in_smem;        // set by launch_binning
 };
 cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand, cudaStream_t stream);
 int binning_blocks_per_sm();
@@ -87,7 +89,7 @@ struct CompositeArgs {
     float clear[4];
     uint32_t tile_y0;             // first tile row to composite (sharded rendering: this rank's band); dst row 0 = that row
     uint32_t *signal_flag;        // optional (peer-mapped): set to signal_epoch by the last CTA once every pixel store is fenced
-    uint32_t signal_epoch;
+    const uint32_t *signal_epoch;  // device word holding the frame number to signal (the frame replays as a CUDA graph)
     uint32_t *done_counter;       // with signal_flag: zeroed per frame
     // occlusion split: mode 0 = the whole list in one pass; 1 = near slab, per-pixel state {r,g,b,T} + per-tile
     // "saturated" flag out, no pixels; 2 = far slab, state in, final pixels out
@@ -145,13 +147,14 @@ struct RouteArgs {
     uint32_t *err;
     // host-collective-free mode: rows, barrier and band signal go through peer-mapped mailboxes
     ShardMailbox *peer_mail[8];                                // NULL: NCCL mode (matrix/totals are plain buffers)
-    uint32_t epoch;                                            // frame number, > 0
+    const uint32_t *epoch_ptr;                                 // device word: frame number, > 0 (advanced by the frame itself)
     uint32_t *done_counter;                                    // zeroed per frame: last-CTA detection
     uint32_t gated;                                            // 1: flag waits run in one-warp gate kernels in front of the consumers
 };
 cudaError_t launch_shard_finish_peer(const RouteArgs &a, uint32_t *vals, const uint32_t *keys, uint32_t *hist, int passes,
                                      FrameCounters *counters, int grid, cudaStream_t stream);
-cudaError_t launch_wait_bands(const ShardMailbox *mail, uint32_t world, uint32_t epoch, uint32_t *err, cudaStream_t stream);
+cudaError_t launch_wait_bands(const ShardMailbox *mail, uint32_t world, const uint32_t *epoch_ptr, uint32_t *err, cudaStream_t stream);
+cudaError_t launch_epoch_advance(uint32_t *epoch, cudaStream_t stream);
 cudaError_t launch_route_count(const RouteArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_route_scatter(const RouteArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_shard_finish(const uint32_t *matrix, uint32_t world, uint32_t rank, uint32_t recv_cap,
