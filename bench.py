@@ -485,7 +485,7 @@ def run_ours(args):
                          "depth_sort": acc["ms_depth_sort"], "binning": acc["ms_binning"],
                          "tile_sort": acc["ms_tile_sort"]},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 448, "d2h_bytes_per_step": W * H * 8,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 480, "d2h_bytes_per_step": W * H * 8,
                 "checksum": checksum, "checksum_what": "CRC-32 of the full RGBA16F frame of view %d" % CHECKSUM_VIEW,
                 "checksum_split_off": checksum_off, "checksum_split_identical": checksum == checksum_off},
         "extra": extra,

@@ -10,3 +10,8 @@ for w in 4 8; do
   nvcc $FLAGS -lineinfo -Xcompiler -fPIC -DWS_LB_WIDTH=$w -c web-splat_b200/csrc/radix_sort.cu -o /tmp/radix_sort_w$w.o
   nvcc $FLAGS profiles/microbench/sort_vs_cub.cu /tmp/radix_sort_w$w.o -o profiles/microbench/sort_vs_cub_w$w
 done
+# occupancy A/B: the pass compiled for 4 resident CTAs per SM (64 registers, second half of the values loaded inside the reorder)
+for w in 4 16; do
+  nvcc $FLAGS -lineinfo -Xcompiler -fPIC -DWS_SORT_CTAS=4 -DWS_LB_WIDTH=$w -c web-splat_b200/csrc/radix_sort.cu -o /tmp/radix_sort_c4w$w.o
+  nvcc $FLAGS profiles/microbench/sort_vs_cub.cu /tmp/radix_sort_c4w$w.o -o profiles/microbench/sort_vs_cub_c4w$w
+done

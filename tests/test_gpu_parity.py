@@ -498,7 +498,7 @@ def test_deferred_frame_status_and_index_validation(ws, ctx):
             assert np.array_equal(t2.cpu().numpy(), img0)
 
 
-@pytest.mark.parametrize("scaling,n,W,H", [(6.0, 3000, 640, 360), (10.0, 700, 1920, 1080), (1.0, 40000, 1200, 799)])
+@pytest.mark.parametrize("scaling,n,W,H", [(6.0, 3000, 640, 360), (10.0, 300, 1920, 1080), (1.0, 40000, 1200, 799)])
 def test_binning_large_rectangles(ws, orc, ctx, scaling, n, W, H):
     """bin_expand: rectangles above 32 tiles are expanded by the whole block, small ones by their owner thread, partitions
     with more than 4096 pairs in several chunks -- the (tile, slot) pair list, ranges and image must not care

@@ -25,6 +25,8 @@
 #include "ws_device.cuh"
 #include "ws_kernels.h"
 
+#include <stdlib.h>
+
 namespace ws {
 
 namespace {
@@ -274,6 +276,134 @@ bin_expand_kernel(BinningArgs a)
     }
 }
 
+constexpr int BIN_ROUNDS = 8;                         // (v1) output positions per thread and chunk
+constexpr int BIN_CAP = BIN_THREADS * BIN_ROUNDS;     // (v1) 2048 pairs per chunk
+// ---- (3') EXPAND, round-1 version (WS_BIN_EXPAND=1): load-balanced over pairs with markers + prefix-max; kept for the A/B in profiles/ ----
+__global__ void __launch_bounds__(BIN_THREADS, 4)
+bin_expand_v1_kernel(BinningArgs a)
+{
+    __shared__ uint32_t s_owner[BIN_CAP];             // marker = owner index + 1 at the owner's first position
+    __shared__ uint4 s_info[BIN_PART];                // per splat: {first pair (block-local), x0 | y0<<16, slot, width}
+    __shared__ uint32_t s_magic[BIN_PART];            // ceil(2^32 / width)
+    __shared__ uint32_t s_hist[BIN_NDIG][256];
+    __shared__ uint32_t s_scan[BIN_WARPS];
+    __shared__ uint32_t s_wcarry[BIN_WARPS];
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t V = a.counters->num_visible;
+    uint32_t lo, hi;
+    slab_bounds(a, V, lo, hi);
+    const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
+    const uint32_t tiles_x = a.uniforms->tiles_x;
+    const uint32_t cap = a.pair_cap;
+    const uint32_t ntiles = tiles_x * a.uniforms->tiles_y;
+    const int ndig = (ntiles > 65536u) ? 3 : ((ntiles > 256u) ? 2 : 1);
+
+    for (unsigned i = tid; i < (unsigned)(BIN_NDIG * 256); i += BIN_THREADS) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
+
+    for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
+        SplatRects r;
+        load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r, a.tile_done ? a.keep4[part * BIN_THREADS + tid] : 0x01010101u);
+        const uint32_t base = __ldg(a.part_bases + part);
+        if (base >= cap) continue;                        // beyond the pair capacity (overflow is already flagged): nothing of this partition is stored
+        const uint32_t mine = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
+        // block scan of the per-thread totals
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < BIN_WARPS; k++) {
+            const uint32_t c = s_scan[k];
+            if (k < (int)warp) woff += c;
+            total += c;
+        }
+        uint32_t excl[BIN_SPT];
+        excl[0] = incl + woff - mine;
+#pragma unroll
+        for (int j = 1; j < BIN_SPT; j++) excl[j] = excl[j - 1] + r.cnt[j - 1];
+#pragma unroll
+        for (int j = 0; j < BIN_SPT; j++) {
+            s_info[tid * BIN_SPT + j] = make_uint4(excl[j], r.xy[j], r.slot[j], r.w[j]);
+            s_magic[tid * BIN_SPT + j] = (r.w[j] > 1u) ? __float2uint_ru(__fdiv_ru(4294967296.f, (float)r.w[j])) : 0u;
+            // m >= 2^32/w with m*w - 2^32 <= w + 512: floor(t/w) == umulhi(t, m) for every t < 2^20, w <= 1024 (viewport <= 16384)
+        }
+
+        for (uint32_t c0 = 0; c0 < total; c0 += BIN_CAP) {
+            const uint32_t m = (total - c0 < (uint32_t)BIN_CAP) ? total - c0 : (uint32_t)BIN_CAP;
+            const uint32_t rounds = (m + BIN_THREADS - 1u) / BIN_THREADS;       // 32-position rounds per warp
+            const uint32_t span = rounds * 32u;                                 // consecutive positions owned by a warp
+            // 1. clear, 2. markers
+            for (uint32_t q = tid; q < m; q += BIN_THREADS) s_owner[q] = 0u;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < BIN_SPT; j++) {
+                if (r.cnt[j] > 0u) {
+                    if (excl[j] >= c0 && excl[j] < c0 + m) s_owner[excl[j] - c0] = tid * BIN_SPT + j + 1u;
+                    else if (excl[j] < c0 && excl[j] + r.cnt[j] > c0) s_owner[0] = tid * BIN_SPT + j + 1u;   // continues from the previous chunk
+                }
+            }
+            __syncthreads();
+            // 3. prefix-max of the markers over this warp's span
+            uint32_t own[BIN_ROUNDS];
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < BIN_ROUNDS; k++) {
+                own[k] = 0u;
+                if ((uint32_t)k < rounds) {
+                    const uint32_t q = warp * span + (uint32_t)k * 32u + lane;
+                    uint32_t v = (q < m) ? s_owner[q] : 0u;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+                        if ((int)lane >= o) v = v > t ? v : t;
+                    }
+                    v = v > carry ? v : carry;
+                    carry = __shfl_sync(0xffffffffu, v, 31);
+                    own[k] = v;
+                }
+            }
+            if (lane == 0) s_wcarry[warp] = carry;
+            __syncthreads();
+            uint32_t prev = 0;
+#pragma unroll
+            for (int k = 0; k < BIN_WARPS; k++) if (k < (int)warp) { const uint32_t c = s_wcarry[k]; prev = prev > c ? prev : c; }
+            // 4. emit: position -> (tile, slot), coalesced, plus the tile-id digit histogram
+#pragma unroll
+            for (int k = 0; k < BIN_ROUNDS; k++) {
+                if ((uint32_t)k < rounds) {
+                    const uint32_t q = warp * span + (uint32_t)k * 32u + lane;
+                    const uint64_t g = (uint64_t)base + c0 + q;
+                    if (q < m && g < cap) {
+                        const uint32_t o = (own[k] > prev ? own[k] : prev) - 1u;
+                        const uint4 inf = s_info[o];
+                        const uint32_t t = c0 + q - inf.x;
+                        const uint32_t ty = (inf.w > 1u) ? __umulhi(t, s_magic[o]) : t;
+                        const uint32_t tx = t - ty * inf.w;
+                        const uint32_t tile = ((inf.y >> 16) + ty) * tiles_x + (inf.y & 0xffffu) + tx;
+                        a.pair_tiles[g] = tile;
+                        a.pair_slots[g] = inf.z;
+                        for (int d = 0; d < ndig; d++) atomicAdd(&s_hist[d][(tile >> (8 * d)) & 255u], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+
+    for (unsigned i = tid; i < (unsigned)(ndig * 256); i += BIN_THREADS) {
+        const uint32_t c = s_hist[i >> 8][i & 255u];
+        if (c) atomicAdd(a.hist + i, c);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand, cudaStream_t stream)
@@ -284,7 +414,9 @@ cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand
     ac.done_in_smem = done_bytes ? 1u : 0u;
     bin_count_kernel<<<grid_count, BIN_THREADS, done_bytes, stream>>>(ac);
     bin_scan_kernel<<<1, 1024, 0, stream>>>(a);
-    bin_expand_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
+    static const int variant = [] { const char *e = getenv("WS_BIN_EXPAND"); return (e && atoi(e) == 1) ? 1 : 2; }();
+    if (variant == 1) bin_expand_v1_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
+    else bin_expand_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

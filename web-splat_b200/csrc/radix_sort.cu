@@ -75,8 +75,11 @@ __device__ __forceinline__ void lookback_level(const uint32_t *col, int p, int l
     }
 }
 
+#ifndef WS_SORT_CTAS
+#define WS_SORT_CTAS 3                         // resident CTAs per SM the pass is compiled for (4 = 64 registers: A/B knob, profiles/microbench)
+#endif
 template <bool EMIT_RANGES, int RANK_WAYS>
-__global__ void __launch_bounds__(SORT_THREADS, 3)   // 16 items x 3 CTAs/SM measured best: 8 items x 4 CTAs and 16 items x 4 CTAs (spilling) were 7-10 % slower
+__global__ void __launch_bounds__(SORT_THREADS, WS_SORT_CTAS)   // round 1: 16 items x 3 CTAs/SM measured best: 8 items x 4 CTAs and 16 items x 4 CTAs (spilling) were 7-10 % slower
 onesweep_pass_kernel(SortPassArgs a)
 {
     __shared__ __align__(16) uint32_t s_keys[SORT_PART];      // during ranking s_keys / s_vals double as the peer masks
@@ -219,13 +222,18 @@ onesweep_pass_kernel(SortPassArgs a)
         st_relaxed(st, (part == 0u ? LB_PREFIX : LB_AGGREGATE) | total);
 
         // values are needed only for the reorder: issue their loads now
+#if WS_SORT_CTAS >= 4
+        constexpr int VAL_NOW = SORT_ITEMS / 2;        // 64-register build: the second half is loaded inside the reorder
+#else
+        constexpr int VAL_NOW = SORT_ITEMS;
+#endif
         uint32_t val[SORT_ITEMS];
         if (full) {
 #pragma unroll
-            for (int i = 0; i < SORT_ITEMS; i++) val[i] = a.vals_in[base + wbase + i * 32u + lane];
+            for (int i = 0; i < VAL_NOW; i++) val[i] = a.vals_in[base + wbase + i * 32u + lane];
         } else {
 #pragma unroll
-            for (int i = 0; i < SORT_ITEMS; i++) {
+            for (int i = 0; i < VAL_NOW; i++) {
                 const uint32_t li = wbase + i * 32u + lane;
                 val[i] = (li < nvalid) ? a.vals_in[base + li] : 0u;
             }
@@ -252,6 +260,13 @@ onesweep_pass_kernel(SortPassArgs a)
 
         // ---- reorder in shared memory (needs only block-local information); meanwhile the
         //      predecessors get time to publish, which shortens the look-back below
+#if WS_SORT_CTAS >= 4
+#pragma unroll
+        for (int i = VAL_NOW; i < SORT_ITEMS; i++) {
+            const uint32_t li = wbase + i * 32u + lane;
+            val[i] = (li < nvalid) ? a.vals_in[base + li] : 0u;
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; i++) {
             const uint32_t d = (key[i] >> shift) & 255u;
