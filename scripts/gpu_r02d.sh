@@ -10,11 +10,13 @@ WS_TEST_CPP_TOOL=1 timeout 1500 python -m pytest tests -m gpu -q -s 2>&1 | grep 
 echo "== bench: expand kernel A/B"
 timeout 300 python bench.py --steps 108 --warmup 5 --no-cpu-baseline --no-extra > $O/r02d_bench_cfg3_expand2.json 2> /dev/null
 WS_BIN_EXPAND=1 timeout 300 python bench.py --steps 108 --warmup 5 --no-cpu-baseline --no-extra > $O/r02d_bench_cfg3_expand1.json 2> /dev/null
+WS_ACTIVE_CULL=0 timeout 300 python bench.py --steps 108 --warmup 5 --no-cpu-baseline --no-extra > $O/r02d_bench_cfg3_nocull.json 2> /dev/null
+WS_ACTIVE_CULL=0 timeout 300 python bench.py --workload cfg4 --steps 72 --warmup 5 --no-cpu-baseline --no-extra > $O/r02d_bench_cfg4_nocull.json 2> /dev/null
 timeout 300 python bench.py --workload cfg4 --steps 72 --warmup 5 --no-cpu-baseline --no-extra > $O/r02d_bench_cfg4_expand2.json 2> /dev/null
 WS_BIN_EXPAND=1 timeout 300 python bench.py --workload cfg4 --steps 72 --warmup 5 --no-cpu-baseline --no-extra > $O/r02d_bench_cfg4_expand1.json 2> /dev/null
 python - <<'PY'
 import json
-for f in ("cfg3_expand2", "cfg3_expand1", "cfg4_expand2", "cfg4_expand1"):
+for f in ("cfg3_expand2", "cfg3_expand1", "cfg3_nocull", "cfg4_expand2", "cfg4_expand1", "cfg4_nocull"):
     try:
         d = json.load(open("gpurun_out/r02d_bench_%s.json" % f))
         print(f, round(d["value"], 1), round(d["e2e"]["value"], 1), {k: round(v, 4) for k, v in d["ms_per_frame"].items() if k != "note"}, d["e2e"].get("checksum"))

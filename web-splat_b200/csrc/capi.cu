@@ -860,6 +860,13 @@ extern "C" ws_status ws_renderer_set_occlusion_split(ws_renderer *r, int32_t ena
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// compositor: cull against the box of still-unsaturated pixels (WS_ACTIVE_CULL=0 turns it off for A/B runs in profiles/)
+static int active_cull_default()
+{
+    static const int v = [] { const char *e = getenv("WS_ACTIVE_CULL"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    return v;
+}
+
 // GPURSSorter::create_sort_stuff analogue (gpu_rs.rs:141-175, renderer.rs:200-211)
 static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
 {
@@ -1106,7 +1113,7 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
         memset(&a, 0, sizeof a);
         a.splats = r->d_splats; a.pair_slots = r->d_pslots[r->tile_out]; a.ranges = r->d_ranges;
         a.uniforms = r->d_uniforms; a.format = (int)r->format;
-        a.mode = 1; a.state = r->d_state; a.tile_done = r->d_tile_done;
+        a.mode = 1; a.state = r->d_state; a.tile_done = r->d_tile_done; a.active_cull = active_cull_default();
         // sharded frames: only this rank's band of tile rows (the received rectangles are clipped to it)
         const bool band = r->shard.world > 0;
         a.tile_y0 = band ? r->shard.band_y0[r->shard.rank] : 0u;
@@ -1573,7 +1580,7 @@ static ws_status enqueue_composite(ws_renderer *r, void *dst, size_t row_pitch, 
         a.mode = 2; a.state = r->d_state; a.tile_done = r->d_tile_done;
     }
     a.uniforms = r->d_uniforms; a.dst = dst; a.row_pitch = (uint32_t)row_pitch; a.format = (int)r->format;
-    a.tile_y0 = tile_y0;
+    a.tile_y0 = tile_y0; a.active_cull = active_cull_default();
     a.signal_flag = r->shard.pending_signal; a.signal_epoch = r->shard.d_epoch; a.done_counter = &r->d_counters->composite_done;
     r->shard.pending_signal = nullptr;
     for (int i = 0; i < 4; i++) a.clear[i] = clear ? (float)clear[i] : 0.f;

@@ -172,12 +172,22 @@ composite_kernel(CompositeArgs a)
                 T -= wt;                                          /* T * (1 - w) */             \
                 T = (T < T_EPS) ? 0.f : T;                                                      \
             }
+            unsigned act = __ballot_sync(0xffffffffu, T != 0.f);        // lanes (pixels) that can still change
             for (int c0 = 0; c0 < cur_cnt; c0 += 32) {
+                // cull against the bounding box of the pixels that are still unsaturated, not the whole 8x4 block: a splat that
+                // only reaches saturated pixels contributes exactly nothing (their T is 0), so skipping it changes no bit
+                float lo_x = blo_x, hi_x = bhi_x, lo_y = blo_y, hi_y = bhi_y;
+                if (a.active_cull && act != 0xffffffffu) {
+                    const unsigned cols = (act | (act >> 8) | (act >> 16) | (act >> 24)) & 0xffu;      // lane = y * 8 + x
+                    const unsigned rows = ((act & 0xffu) ? 1u : 0u) | ((act & 0xff00u) ? 2u : 0u) | ((act & 0xff0000u) ? 4u : 0u) | ((act >> 24) ? 8u : 0u);
+                    lo_x = blo_x + (float)(__ffs(cols) - 1); hi_x = blo_x + (float)(31 - __clz(cols));
+                    lo_y = blo_y + (float)(__ffs(rows) - 1); hi_y = blo_y + (float)(31 - __clz(rows));
+                }
                 const int k = c0 + (int)lane;
                 bool hit = false;
                 if (k < cur_cnt) {
                     const float4 D = sd[k];
-                    hit = (D.x + D.z >= blo_x) && (D.x - D.z <= bhi_x) && (D.y + D.w >= blo_y) && (D.y - D.w <= bhi_y);
+                    hit = (D.x + D.z >= lo_x) && (D.x - D.z <= hi_x) && (D.y + D.w >= lo_y) && (D.y - D.w <= hi_y);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
                 while (m) {                                             // two hits per trip: front-to-back order is kept
@@ -190,7 +200,8 @@ composite_kernel(CompositeArgs a)
                         WS_EVAL(j1)
                     }
                 }
-                if (__all_sync(0xffffffffu, T == 0.f)) break;
+                act = __ballot_sync(0xffffffffu, T != 0.f);
+                if (act == 0u) break;
             }
 #undef WS_EVAL
         }

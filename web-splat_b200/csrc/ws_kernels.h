@@ -94,6 +94,7 @@ struct CompositeArgs {
     // occlusion split: mode 0 = the whole list in one pass; 1 = near slab, per-pixel state {r,g,b,T} + per-tile
     // "saturated" flag out, no pixels; 2 = far slab, state in, final pixels out
     int mode;
+    int active_cull;              // per-warp cull against the bounding box of the still-unsaturated pixels (result-neutral)
     float4 *state;                // W x H
     uint8_t *tile_done;           // T
 };
