@@ -403,7 +403,7 @@ def run_ours(args):
         if args.workload == "cfg3" and split:
             tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic_cfg3_split.json")))
             traffic = tj["per_stage"][dom]["dram_bytes"]
-            traffic_src = "profiles/kernel_traffic_cfg3_split.json (ncu --set full, r01q, occlusion split: %s)" % tj["per_stage"][dom]["launches"]
+            traffic_src = "profiles/kernel_traffic_cfg3_split.json (%s; %s)" % (tj.get("source", "ncu --set full"), tj["per_stage"][dom]["launches"])
         elif args.workload == "cfg3":
             tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic_cfg3.json")))
             key = {"composite": "composite_kernel<1>", "preprocess": "preprocess_kernel<0>", "binning": "bin_expand_kernel",

@@ -2,7 +2,10 @@
 """Per-launch table of an `ncu --set full` report (one frame of bench.py): duration, issue-slot utilisation, pipe
 utilisation (FMA / ALU / XU = MUFU / LSU / uniform), shared-memory wavefront pipe, DRAM bytes and throughput, occupancy
 limiter -- the numbers DESIGN.md and bench.py's `composite_pipes` quote.
-usage: ncu_summary.py report.ncu-rep [out_prefix]   -> prints markdown; with out_prefix also writes <out_prefix>.json"""
+usage: ncu_summary.py report.ncu-rep [out_prefix] [--bench WORKLOAD "source note"]
+  prints markdown; with out_prefix also writes <out_prefix>.json; with --bench (a capture of ONE split frame of that
+  workload, 19 launches) also rewrites the two files bench.py reads: profiles/kernel_traffic_<workload>_split.json (DRAM
+  bytes per launch and per stage) and profiles/composite_pipes_<workload>.json (measured issue / pipe utilisation)."""
 import csv
 import io
 import json
@@ -71,8 +74,35 @@ def main():
         cells = [rec["kernel"]] + [("%.1f" % rec[c[0]]) if rec[c[0]] is not None else "" for c in COLS]
         cells.append(", ".join("%s %.2f" % kv for kv in rec["stalls_per_issue"].items()))
         print("| %d | " % i + " | ".join(cells) + " |")
-    if len(sys.argv) > 2:
+    if len(sys.argv) > 2 and not sys.argv[2].startswith("--"):
         json.dump(table, open(sys.argv[2] + ".json", "w"), indent=1)
+    if "--bench" in sys.argv:
+        import os
+        i = sys.argv.index("--bench")
+        wl, note = sys.argv[i + 1], sys.argv[i + 2]
+        here = os.path.dirname(os.path.abspath(__file__))
+        per = [{"index": k, "kernel": t["kernel"], "us": round(t["us"], 1), "dram_read_bytes": t["DRAM rd MB"] * 1e6, "dram_write_bytes": t["DRAM wr MB"] * 1e6} for k, t in enumerate(table)]
+        tot = lambda rows: sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows)
+        pick = lambda name: [r for r in per if r["kernel"].startswith(name)]
+        comp = pick("composite_kernel"); sweeps = pick("onesweep")
+        depth, tile = sweeps[:4], sweeps[4:]
+        stage = {
+            "preprocess": {"dram_bytes": tot(pick("count_kernel") + pick("scan_kernel") + pick("preprocess_kernel")), "launches": "count + scan + preprocess"},
+            "depth_sort_pass": {"dram_bytes": tot(depth) / max(len(depth), 1), "launches": "average of the 4 depth passes"},
+            "binning": {"dram_bytes": tot(pick("bin_")), "launches": "count + scan + expand, both slabs"},
+            "tile_sort_pass": {"dram_bytes": tot(tile) / 2.0, "launches": "both slabs, per pass position (2 positions)"},
+            "composite": {"dram_bytes": tot(comp), "launches": "near slab (state out) + far slab (state in, pixels out)"},
+        }
+        json.dump({"source": note, "per_launch": per, "per_stage": stage}, open(os.path.join(here, "kernel_traffic_%s_split.json" % wl), "w"), indent=1)
+        near = max((t for t in table if t["kernel"].startswith("composite_kernel")), key=lambda t: t["us"])
+        pipes = {"kernel": near["kernel"] + " (near slab: 95 % of the compositor's time)", "us_under_ncu": round(near["us"], 1),
+                 "issue_slots_pct_of_peak": round(near["issue %"], 1), "warp_instructions_M": round(near["warp-instr M"], 1),
+                 "pipe_fma_pct": round(near["fma %"], 1), "pipe_alu_pct": round(near["alu %"], 1), "pipe_xu_mufu_pct": round(near["xu %"], 1),
+                 "pipe_lsu_pct": round(near["lsu %"], 1), "pipe_uniform_pct": round(near["uniform %"], 1),
+                 "shared_memory_wavefronts_pct": round(near["smem wavefronts %"], 1), "dram_pct": round(near["DRAM %"], 1),
+                 "stalls_per_issue": near["stalls_per_issue"],
+                 "reading": "issue-bound: the schedulers issue on >80 % of the cycles; MUFU (ex2) runs at a fifth of its rate, DRAM at a twentieth"}
+        json.dump({"source": note, "metrics": pipes}, open(os.path.join(here, "composite_pipes_%s.json" % wl), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -15,10 +15,16 @@
 // ticket / gather / look-back round trips and the kernel ran at 8 % of the HBM roofline):
 //   COUNT   pairs per 1024-splat partition (slot load + rectangle gather, 4 per thread in flight);
 //   SCAN    one CTA: exclusive scan of the partition totals, P, overflow flag;
-//   EXPAND  pairs are staged in shared memory at their block-local output position (scan of the
-//           per-splat counts) and leave as perfectly coalesced stores; a splat's owner thread walks
-//           its rectangle (3.5 tiles on average), rectangles above 32 tiles are walked by the whole
-//           block together, so a screen-filling splat costs no more than its share of positions.
+//   EXPAND  load-balanced over PAIRS, not splats: every splat with at least one tile drops a
+//           marker (its index) at the block-local offset of its first pair, a prefix-max over
+//           the positions (warp shuffles, 8 positions per thread) tells every output position
+//           which splat owns it, and the thread derives (tile x, tile y) from the position with
+//           one multiply-high (magic reciprocal of the rectangle width).  Threads emit
+//           consecutive pairs straight to global memory, perfectly coalesced, however uneven
+//           the rectangles are (a screen-filling splat simply owns many consecutive positions).
+//           (A round-2 rewrite -- owner thread walks its rectangle, the block walks the large ones,
+//           pairs staged in shared memory -- is kept as bin_expand_kernel / WS_BIN_EXPAND=2: it
+//           executes a quarter of the instructions and is 13 % slower, profiles/r02d_*.)
 // The digit histogram uses plain shared-memory atomicAdd (no return value): measured at
 // 118-135 G warp-ops/s on B200 whatever the address spread, 25x a MATCH.ANY-aggregated update
 // (profiles/microbench/rank_primitives.cu).
@@ -150,8 +156,8 @@ bin_scan_kernel(BinningArgs a)
     }
 }
 
-// ---- (3) EXPAND ----------------------------------------------------------------------------------
-// Round 2 rewrite.  ncu on the round-1 kernel (profiles/r02a: 139 lane-instructions per emitted pair, 1168 SASS
+// ---- (3'') EXPAND, round-2 rewrite (WS_BIN_EXPAND=2; NOT the default: measured slower, see launch_binning) -------------
+// ncu on the round-1 kernel (profiles/r02a: 139 lane-instructions per emitted pair, 1168 SASS
 // instructions, the marker / prefix-max machinery executed for every output position) showed the general
 // load-balancing scheme costing 3x what the data needs: a splat touches 3.5 tiles on average, so the owner thread
 // simply walks its own rectangle.  Only rectangles above EXP_SMALL tiles (close-ups, gaussian_scaling > 1) are expanded
@@ -278,7 +284,7 @@ bin_expand_kernel(BinningArgs a)
 
 constexpr int BIN_ROUNDS = 8;                         // (v1) output positions per thread and chunk
 constexpr int BIN_CAP = BIN_THREADS * BIN_ROUNDS;     // (v1) 2048 pairs per chunk
-// ---- (3') EXPAND, round-1 version (WS_BIN_EXPAND=1): load-balanced over pairs with markers + prefix-max; kept for the A/B in profiles/ ----
+// ---- (3) EXPAND (default): load-balanced over PAIRS with markers + prefix-max -----------------------------------------
 __global__ void __launch_bounds__(BIN_THREADS, 4)
 bin_expand_v1_kernel(BinningArgs a)
 {
@@ -414,7 +420,10 @@ cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand
     ac.done_in_smem = done_bytes ? 1u : 0u;
     bin_count_kernel<<<grid_count, BIN_THREADS, done_bytes, stream>>>(ac);
     bin_scan_kernel<<<1, 1024, 0, stream>>>(a);
-    static const int variant = [] { const char *e = getenv("WS_BIN_EXPAND"); return (e && atoi(e) == 1) ? 1 : 2; }();
+    // default: the round-1 kernel (markers + prefix-max).  Measured on B200 (profiles/r02d_*): 80.0 vs 90.7 us for the near
+    // slab of cfg3, binning 0.309 vs 0.399 ms at cfg4 -- the round-2 rewrite executes a quarter of the instructions but its
+    // owner-thread loops serialise on the longest rectangle of each warp and its scattered staging stores conflict.
+    static const int variant = [] { const char *e = getenv("WS_BIN_EXPAND"); return (e && atoi(e) == 2) ? 2 : 1; }();
     if (variant == 1) bin_expand_v1_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
     else bin_expand_kernel<<<grid_expand, BIN_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
@@ -423,7 +432,7 @@ cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand
 int binning_blocks_per_sm()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bin_expand_kernel, BIN_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bin_expand_v1_kernel, BIN_THREADS, 0);
     return nb > 0 ? nb : 1;
 }
 
