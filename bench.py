@@ -89,6 +89,12 @@ class ClockSampler(threading.Thread):
                 pass
             self._halt.wait(0.01)
 
+    def reset(self):
+        """forget the samples taken so far (the sampler is started BEFORE the barrier in front of a timed region -- its NVML
+        initialisation costs milliseconds on the one rank that runs it, which every other rank of a multi-GPU run would
+        otherwise spend waiting inside ITS timed region -- and reset right at the region's start)"""
+        self.rows = []
+
     def finish(self):
         self._halt.set()
         self.join(timeout=6)

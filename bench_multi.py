@@ -122,10 +122,12 @@ def run(args):
         torch.cuda.synchronize()
         checksum_n1 = bench.frame_crc(chk)
         del plain, fpc, fgen, full
-    sync_all()
-    sampler = bench.ClockSampler(local) if rank == 0 else None
-    if sampler:
+    sampler = bench.ClockSampler(local) if rank == 0 else None      # NVML init + thread start BEFORE the barrier: rank 0 alone pays
+    if sampler:                                                     # them, and the other ranks would wait for it inside their timed region
         sampler.start()
+    sync_all()
+    if sampler:
+        sampler.reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cur = torch.cuda.current_stream()
     e0.record(cur)
