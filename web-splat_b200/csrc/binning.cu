@@ -49,7 +49,9 @@ struct SplatRects { uint32_t slot[BIN_SPT], xy[BIN_SPT], w[BIN_SPT], h[BIN_SPT],
 // the split point is a multiple of 4 so that the 16-byte slot loads stay aligned
 __device__ __forceinline__ void slab_bounds(const BinningArgs &a, uint32_t V, uint32_t &lo, uint32_t &hi)
 {
-    const uint32_t split = (V >> 1) & ~3u;
+    // the nearest near_pct % of the depth-sorted splats form the near slab (0 = the default half)
+    const uint32_t near = a.near_pct ? (uint32_t)(((uint64_t)V * a.near_pct) / 100u) : (V - (V >> 1));
+    const uint32_t split = (V - near) & ~3u;
     lo = (a.slab == 1u) ? split : 0u;
     hi = (a.slab == 2u) ? split : V;
 }

@@ -860,6 +860,13 @@ extern "C" ws_status ws_renderer_set_occlusion_split(ws_renderer *r, int32_t ena
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// occlusion split: percentage of the depth-sorted splats that form the near slab (WS_SPLIT_NEAR_PCT; 0 / unset = half)
+static uint32_t split_near_pct()
+{
+    static const uint32_t v = [] { const char *e = getenv("WS_SPLIT_NEAR_PCT"); const int p_ = e ? atoi(e) : 0; return (p_ >= 5 && p_ <= 95) ? (uint32_t)p_ : 0u; }();
+    return v;
+}
+
 // compositor: cull against the box of still-unsaturated pixels (WS_ACTIVE_CULL=0 turns it off for A/B runs in profiles/)
 static int active_cull_default()
 {
@@ -918,7 +925,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
             CU(cudaMalloc(&r->d_pslots[i], (size_t)pair_cap * 4));
         }
         CU(cudaMalloc(&r->d_rects, nn * 8));
-        CU(cudaMalloc(&r->d_keep4, (nn / 2 + 2 * 1024 + 4) / 4 * 4 + 4096));   // far slab rounded up to whole 1024-splat partitions
+        CU(cudaMalloc(&r->d_keep4, (nn + 2 * 1024 + 4) / 4 * 4 + 4096));   // one byte per far-slab splat (the far slab may be most of the cloud), rounded up to whole 1024-splat partitions
         r->n_cap = n; r->pair_cap = pair_cap;
         r->buf_generation = next_generation();
     }
@@ -1077,6 +1084,7 @@ static ws_status enqueue_stage2(ws_renderer *r, cudaStream_t stream)
             a.slab = slab; a.tile_done = (slab == 2u) ? r->d_tile_done : nullptr; a.pair_cap = cap; a.num_pairs_out = num_pairs;
             a.keep4 = r->d_keep4;
             a.num_tiles_hint = r->h_uniforms.tiles_x * r->h_uniforms.tiles_y; a.done_in_smem = 0;
+            a.near_pct = split_near_pct();
             CU(launch_binning(a, r->ctx->sm_count * 8, r->grid_bin, stream));
         }
         if (r->timing) CU(cudaEventRecord(r->ev[ev_bin], stream));
