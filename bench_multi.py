@@ -59,7 +59,9 @@ def run(args):
     N = int(cloud["num_points"])
     depth = int(getattr(args, "frames_in_flight", 0) or 0)
     if depth <= 0:
-        depth = 3 if world >= 8 else 2       # measured on cfg3: 8 GPUs 1916 (1 in flight) -> 2434 (2) -> 2691 (3) frames/s
+        # the smaller a GPU's share, the more latency-bound a single frame is and the more frames fit next to each other.
+        # Measured on cfg3 (profiles/r02h_*, r02e_*): 8 GPUs 2866 (3 in flight) -> 3275 (4) -> 3414 (5) frames/s; 4 GPUs 1843 (2) -> 2080 (3)
+        depth = 5 if world >= 8 else (3 if world >= 4 else 2)
     pipe = ws.ShardedPipeline(ws, ctx, fmt, cloud["sh_deg"], cloud["compressed"], pc, N, (W, H), depth=depth,
                               pair_capacity=min(max(8 * N // world + (1 << 22), 1 << 22), (1 << 30) - 1))
     sh = pipe.slots[0]                       # slot 0 also serves the single-frame breakdowns below

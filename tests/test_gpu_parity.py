@@ -171,7 +171,7 @@ def test_options_clipping_box_and_background(ws, orc, ctx):
 
 def test_occlusion_split_is_bit_identical(ws, orc, ctx):
     """Two depth slabs with saturated-tile culling of the far one: same pixels, bit for bit, from fewer pairs."""
-    cases = [(ws.synth.make_cloud(150000, 21), 320, 200, 30.0, ws.FORMAT_RGBA32_FLOAT),      # dense: most tiles saturate
+    cases = [(ws.synth.make_cloud(150000, 21), 80, 50, 30.0, ws.FORMAT_RGBA32_FLOAT),        # ~400 layers per pixel: the near slab saturates every tile
              (ws.synth.make_cloud(150000, 21), 320, 200, 200.0, ws.FORMAT_RGBA16_FLOAT),
              (ws.synth.make_cloud(20000, 22), 800, 600, 75.0, ws.FORMAT_RGBA8_UNORM),        # sparse: few do
              (ws.synth.make_cloud_compressed(60000, 23), 640, 360, 140.0, ws.FORMAT_RGBA32_FLOAT),

@@ -1711,7 +1711,7 @@ extern "C" ws_status ws_renderer_stats(ws_renderer *r, ws_frame_stats *s)
     s->bytes_sort = (uint64_t)r->depth_passes * V * 16 + V * 12 + P * 8 + (uint64_t)r->tile_passes * P * 16 + T * 8;
     s->bytes_blend = P * 24 + T * 8 + (uint64_t)U.width * U.height * bytes_per_pixel(r->format);
     if (r->frame_split) {                                         // the far slab re-reads the slots + rectangles, the state goes out and in
-        s->bytes_sort += (V / 2) * 12;
+        s->bytes_sort += (V - V / 4) * 12;
         s->bytes_blend += T * 8 + (uint64_t)U.width * U.height * 32;
     }
     if (c.error_flags) return fail(WS_ERR_CUDA, (c.error_flags & 2u) ? "sharded frame: receive capacity exceeded" : ((c.error_flags & 4u) ? "sharded frame: a peer never arrived" : "internal: decoupled look-back watchdog fired"));

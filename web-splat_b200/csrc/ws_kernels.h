@@ -66,7 +66,7 @@ struct BinningArgs {
     uint32_t *part_bases;         // ceil(N/1024): exclusive scan (scan kernel)
     uint32_t *hist;               // 4 x 256 tile-id digit histograms (zeroed per frame)
     // occlusion split: the depth-sorted splats are binned in two slabs, nearest first
-    uint32_t slab;                // 0: all of [0, V);  1: the near slab [split, V);  2: the far slab [0, split),  split = (V/2) & ~3
+    uint32_t slab;                // 0: all of [0, V);  1: the near slab [split, V);  2: the far slab [0, split),  split = (V - near) & ~3, near = V/4 unless near_pct is set
     const uint8_t *tile_done;     // slab 2: tiles already saturated by the near slab; a splat whose whole rectangle is done emits no pair
     uint32_t *keep4;              // slab 2: ceil(V/2/4) words, one byte per splat: count kernel -> expand kernel
     uint32_t pair_cap;            // capacity of pair_tiles / pair_slots for this launch
