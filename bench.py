@@ -514,7 +514,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the `measure`-equivalent line (2048^2, RGBA8) under `extra`")
     ap.add_argument("--frames-in-flight", type=int, default=0,
-                    help="frames in flight per GPU (one renderer + stream per frame slot); 0 = auto: 2 (3 at 4 GPUs, 5 at 8 GPUs) "
+                    help="frames in flight per GPU (one renderer + stream per frame slot); 0 = auto: 2 on one GPU, 3 on 2-4 GPUs, 4 on 8 GPUs "
                          "(the smaller the per-GPU share, the more latency-bound a single frame is)")
     ap.add_argument("--no-occlusion-split", action="store_true", help="single-GPU arm: bin / tile-sort / composite all pairs in one pass")
     ap.add_argument("--equal-bands", action="store_true", help="multi-GPU arm: keep the equal tile-row split instead of cost-balanced bands")

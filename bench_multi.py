@@ -60,8 +60,11 @@ def run(args):
     depth = int(getattr(args, "frames_in_flight", 0) or 0)
     if depth <= 0:
         # the smaller a GPU's share, the more latency-bound a single frame is and the more frames fit next to each other.
-        # Measured on cfg3 (profiles/r02h_*, r02e_*): 8 GPUs 2866 (3 in flight) -> 3275 (4) -> 3414 (5) frames/s; 4 GPUs 1843 (2) -> 2080 (3)
-        depth = 5 if world >= 8 else (3 if world >= 4 else 2)
+        # Measured on cfg3 (profiles/r02h_*, r02j_*, 108 timed frames): 8 GPUs 3107* (3 in flight) / 3275 (4) / 3414 (5) / 3357 (6) /
+        # 3366 (8) frames/s; 4 GPUs 1843** (2) / 2080 (3) / 2102 (4); 2 GPUs 1264** (2) / 1363 (3) / 1338 (4).  A deeper pipeline
+        # also ramps up longer, which a 20-frame run sees (8 GPUs, 20 frames: 3107 with 3 in flight, 2920 with 6), hence 4 at 8 GPUs.
+        # (* 20 frames; ** before the near-slab / sampler changes of the same round)
+        depth = 4 if world >= 8 else 3
     pipe = ws.ShardedPipeline(ws, ctx, fmt, cloud["sh_deg"], cloud["compressed"], pc, N, (W, H), depth=depth,
                               pair_capacity=min(max(8 * N // world + (1 << 22), 1 << 22), (1 << 30) - 1))
     sh = pipe.slots[0]                       # slot 0 also serves the single-frame breakdowns below

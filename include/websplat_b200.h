@@ -265,7 +265,7 @@ WS_API ws_status ws_renderer_set_timing(ws_renderer *r, int32_t enabled);
 WS_API ws_status ws_renderer_set_cuda_graphs(ws_renderer *r, int32_t enabled);
 /* Occlusion split (single-GPU frames; enabled: 0 off, 1 on, negative = automatic, the default: on for clouds of at least
  * 2 M points, where the pairs it saves outweigh its six extra launches): the depth-sorted splats are binned, tile-sorted and composited
- * in two slabs, nearest half first; a splat of the far half whose tiles were all saturated by the near half emits no
+ * in two slabs, the nearest quarter first; a splat of the far slab whose tiles were all saturated by the near slab emits no
  * (tile, splat) pair.  Per pixel the blends and early-out tests are those of the one-pass frame: the image is
  * bit-identical, while num_pairs counts only the pairs that were emitted.  Turn it off to get the complete pair list
  * in the WS_BUF_PAIR_* / WS_BUF_TILE_RANGES read-backs (with the split they describe the far slab). */
