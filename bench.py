@@ -432,7 +432,10 @@ def run_ours(args):
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "bytes_formula": "SURVEY.md 8(d): blend = P*(4+20) + T*8 + W*H*B_fmt with P = pairs emitted; no state round trip",
         "note": "stage 3 is FP32/MUFU-issue bound, not HBM bound (SURVEY 8(d)); its HBM fraction is reported because "
-                "the north star asks for it; 'composite_pipes' holds the measured issue / pipe utilisation (ncu)",
+                "the north star asks for it; 'composite_pipes' holds the measured issue / pipe utilisation (ncu). `frac` prices the "
+                "pairs actually EMITTED (%.1f M of the %.1f M of the complete list: the occlusion split drops the rest before they "
+                "are sorted), so it falls when the split removes bytes faster than time; `frac_full_pairs` prices the same time at "
+                "the complete pair list" % (P / 1e6, P_full / 1e6),
         "sort_plus_blend": {"bytes": sb_bytes, "ms": sb_ms, "gbs": gbs(sb_bytes, sb_ms), "frac": gbs(sb_bytes, sb_ms) / peak,
                             "frac_full_pairs": gbs(sb_bytes_full, sb_ms) / peak},
         "composite_pipes": pipes, "composite_pipes_source": pipes_src,
