@@ -42,3 +42,29 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
         pass
     p = _run("--workload", "cfg1", "--steps", "1")
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_reference_arm_sets_its_own_thread_count():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm (and the GPU arm's cpu_baseline) must not inherit
+    it -- round 1's N >= 2 reference lines ran on one core."""
+    p = _run("--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0", env={"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2"})
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    try:
+        want = len(os.sched_getaffinity(0))
+    except AttributeError:
+        want = os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == want
+
+
+def test_frame_crc_is_a_full_frame_hash():
+    """the parity evidence carried by the bench lines: every byte of the downloaded frame enters the checksum"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    a = np.zeros((64, 48, 4), np.float16)
+    c0 = bench.frame_crc(a)
+    for y, x, ch in ((0, 0, 0), (63, 47, 3), (31, 7, 2)):
+        b = a.copy(); b[y, x, ch] = np.float16(6.1e-5)
+        assert bench.frame_crc(b) != c0
+    assert bench.frame_crc(a.copy()) == c0 and len(c0) == 8

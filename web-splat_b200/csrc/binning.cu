@@ -86,7 +86,9 @@ __device__ __forceinline__ void load_rects(const BinningArgs &a, uint32_t first,
 // far slab: a splat all of whose tiles were saturated by the near slab cannot change a pixel.  Only small rectangles are
 // tested (they are almost all of them); a pair emitted for a saturated tile is harmless, the compositor skips that tile.
 // Returns the keep bytes for load_rects (the expand kernel does not repeat the test, nor fetch the dropped rectangles).
-__device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRects &r, const uint8_t *done)
+// `done` is the per-tile byte map (global memory, or its copy in shared memory); `bits`, when not NULL, is the same map as
+// one BIT per tile in shared memory: a row of up to 16 tiles is then one funnel-shifted compare instead of a byte per tile.
+__device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRects &r, const uint8_t *done, const uint32_t *bits)
 {
     const uint32_t tiles_x = a.uniforms->tiles_x;
     uint32_t keep4 = 0u;
@@ -95,8 +97,18 @@ __device__ __forceinline__ uint32_t drop_saturated(const BinningArgs &a, SplatRe
         if (r.cnt[j] > 0u && r.cnt[j] <= 16u) {
             const uint32_t x0 = r.xy[j] & 0xffffu, y0 = r.xy[j] >> 16;
             bool all = true;
-            for (uint32_t yy = 0; yy < r.h[j]; yy++)
-                for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (done[(y0 + yy) * tiles_x + x0 + xx] != 0);
+            if (bits) {
+                const uint32_t mask = (1u << r.w[j]) - 1u;             // w <= 16
+                uint32_t b0 = y0 * tiles_x + x0;
+                for (uint32_t yy = 0; yy < r.h[j]; yy++, b0 += tiles_x) {
+                    const uint32_t w0 = b0 >> 5;
+                    const uint32_t row = __funnelshift_r(bits[w0], bits[w0 + 1u], b0 & 31u);   // bit i = tile b0 + i
+                    all = all && ((row & mask) == mask);
+                }
+            } else {
+                for (uint32_t yy = 0; yy < r.h[j]; yy++)
+                    for (uint32_t xx = 0; xx < r.w[j]; xx++) all = all && (done[(y0 + yy) * tiles_x + x0 + xx] != 0);
+            }
             if (all) r.cnt[j] = 0u;
         }
         if (r.cnt[j] > 0u) keep4 |= 1u << (8 * j);
@@ -115,21 +127,38 @@ bin_count_kernel(BinningArgs a)
     uint32_t lo, hi;
     slab_bounds(a, V, lo, hi);
     const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
-    // The saturation test reads one byte per tile of every small rectangle: random gathers (r02a: 43 us for the far half
-    // of cfg3, long_scoreboard 10 warps per issue).  The whole map is 8 KB at 1080p, 32 KB at 4K: stage it per CTA.
+    // The saturation test reads the "saturated" flag of every tile of every small rectangle: random byte gathers from
+    // global memory in round 1 (r02a: 43 us for the far half of cfg3, long_scoreboard 10 warps per issue).  The whole map is
+    // 8160 tiles at 1080p, 32 400 at 4K: each CTA packs it into ONE BIT per tile in shared memory (1-4 KB), and a rectangle
+    // row becomes two shared-memory words and a funnel shift.
     const uint8_t *done = a.tile_done;
+    const uint32_t *bits = nullptr;
     if (a.tile_done && a.done_in_smem) {
+        uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_done);
         const uint32_t T = a.uniforms->tiles_x * a.uniforms->tiles_y;
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.tile_done);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_done);
-        for (uint32_t i = tid; i < (T + 15u) / 16u; i += BIN_THREADS) dst[i] = src[i];     // the allocation is padded to 16 B
+        const uint32_t nwords = (T + 31u) / 32u;
+        for (uint32_t w = tid; w <= nwords; w += BIN_THREADS) {         // one word past the end stays 0: the funnel shift reads w0 + 1
+            uint32_t v = 0u;
+            if (w < nwords) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.tile_done + (size_t)w * 32u);   // 32 flag bytes (allocation padded)
+                const uint4 q0 = src[0], q1 = src[1];
+                const uint32_t b[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {                          // byte i of the 32 -> bit i (flags are 0 / 1)
+                    v |= ((b[k] & 0x1u) | ((b[k] >> 7) & 0x2u) | ((b[k] >> 14) & 0x4u) | ((b[k] >> 21) & 0x8u)) << (4 * k);
+                }
+                const uint32_t valid = T - w * 32u;                     // tiles beyond T (padding bytes) never count as done... nor matter
+                if (valid < 32u) v &= (1u << valid) - 1u;
+            }
+            s_bits[w] = v;
+        }
         __syncthreads();
-        done = s_done;
+        bits = s_bits;
     }
     for (uint32_t part = blockIdx.x; part < nparts; part += gridDim.x) {
         SplatRects r;
         load_rects(a, lo + part * BIN_PART + tid * BIN_SPT, hi, r);
-        if (a.tile_done) a.keep4[part * BIN_THREADS + tid] = drop_saturated(a, r, done);
+        if (a.tile_done) a.keep4[part * BIN_THREADS + tid] = drop_saturated(a, r, done, bits);
         uint32_t c = r.cnt[0] + r.cnt[1] + r.cnt[2] + r.cnt[3];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -153,7 +182,7 @@ bin_scan_kernel(BinningArgs a)
     uint32_t lo, hi;
     slab_bounds(a, V, lo, hi);
     const uint32_t nparts = (hi - lo + BIN_PART - 1u) / BIN_PART;
-    const uint64_t total_out = block_exclusive_scan_1024(a.part_counts, a.part_bases, nparts);
+    const uint64_t total_out = block_exclusive_scan_1024<uint64_t>(a.part_counts, a.part_bases, nparts);
     if (threadIdx.x == 0) {
         const uint64_t P = (nparts > 0u) ? total_out : 0ull;           // 64-bit: screen-filling splats can push P past 2^32
         *a.num_pairs_out = P > 0xffffffffull ? 0xffffffffu : (uint32_t)P;
@@ -421,7 +450,9 @@ cudaError_t launch_binning(const BinningArgs &a, int grid_count, int grid_expand
 {
     // far slab: the tile_done map travels in dynamic shared memory when it fits under the 48 KB default limit
     BinningArgs ac = a;
-    const size_t done_bytes = (a.tile_done && a.num_tiles_hint && a.num_tiles_hint <= 40000u) ? ((size_t)a.num_tiles_hint + 15u) / 16u * 16u : 0u;
+    // (one bit per tile + one spare word; up to 16384 x 16384 pixels = 1 Mi tiles = 128 KB would not fit the default 48 KB: above
+    // 256 Ki tiles the kernel reads the byte map from global memory)
+    const size_t done_bytes = (a.tile_done && a.num_tiles_hint && a.num_tiles_hint <= 262144u) ? (((size_t)a.num_tiles_hint + 31u) / 32u + 1u) * 4u : 0u;
     ac.done_in_smem = done_bytes ? 1u : 0u;
     bin_count_kernel<<<grid_count, BIN_THREADS, done_bytes, stream>>>(ac);
     bin_scan_kernel<<<1, 1024, 0, stream>>>(a);

@@ -933,7 +933,7 @@ static ws_status ensure_capacity(ws_renderer *r, uint32_t n, uint32_t tiles)
         cudaFree(r->d_ranges); r->d_ranges = nullptr;
         CU(cudaMalloc(&r->d_ranges, (size_t)(tiles ? tiles : 1) * 8 * 2));      // [tiles] near / only, [tiles] far slab
         cudaFree(r->d_tile_done); r->d_tile_done = nullptr;
-        CU(cudaMalloc(&r->d_tile_done, (size_t)(tiles ? tiles : 1) + 16));     // + 16: bin_count stages it with 128-bit loads
+        CU(cudaMalloc(&r->d_tile_done, (size_t)(tiles ? tiles : 1) + 64));     // + 64: bin_count packs it 32 bytes at a time with 128-bit loads
         r->tiles_cap = tiles;
         r->buf_generation = next_generation();
     }

@@ -403,8 +403,8 @@ scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, c
 {
     const uint32_t n = uniforms->num_points;
     const uint32_t nparts = (n + PP_THREADS - 1u) / PP_THREADS;
-    const uint64_t total = block_exclusive_scan_1024(counts, bases, nparts);
-    if (threadIdx.x == 0) counters->num_visible = (uint32_t)total;     // <= N < 2^32
+    const uint32_t total = block_exclusive_scan_1024<uint32_t>(counts, bases, nparts);      // <= N < 2^32: 32-bit scan
+    if (threadIdx.x == 0) counters->num_visible = total;
 }
 
 // ---- (3) MAIN ---------------------------------------------------------------------------------

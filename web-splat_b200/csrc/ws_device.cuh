@@ -183,13 +183,15 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t *flag, uint32_t epoch,
 // 64 bits: pair counts can exceed 2^32 (screen-filling splats); bases saturate at 0xffffffff, which every consumer
 // treats as "beyond capacity", so an overflow is reported instead of wrapping into a silently wrong frame.
 // counts / bases must be 16-byte aligned (they are 256-byte aligned slices of the scratch allocation).
-__device__ __forceinline__ uint64_t block_exclusive_scan_1024(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, uint32_t n)
+// ACC = uint64_t where the total can exceed 2^32 (pair counts), uint32_t where it cannot (survivor counts <= N).
+template <typename ACC>
+__device__ __forceinline__ ACC block_exclusive_scan_1024(const uint32_t *__restrict__ counts, uint32_t *__restrict__ bases, uint32_t n)
 {
     constexpr int E = 16;
-    __shared__ uint64_t s_w[32];
-    __shared__ uint64_t s_tot, s_carry;
+    __shared__ ACC s_w[32];
+    __shared__ ACC s_tot, s_carry;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_carry = 0ull;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 1024u * E) {
         const uint32_t i0 = base + tid * E;
@@ -202,41 +204,41 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_1024(const uint32_t *__
 #pragma unroll
             for (int k = 0; k < E; k++) c[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
         }
-        uint64_t sum = 0;
+        ACC sum = 0;
 #pragma unroll
         for (int k = 0; k < E; k++) sum += c[k];
-        uint64_t incl = sum;
+        ACC incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            const ACC t = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)lane >= o) incl += t;
         }
         if (lane == 31) s_w[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const uint64_t v = s_w[lane];
-            uint64_t vi = v;
+            const ACC v = s_w[lane];
+            ACC vi = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t t = __shfl_up_sync(0xffffffffu, vi, o);
+                const ACC t = __shfl_up_sync(0xffffffffu, vi, o);
                 if ((int)lane >= o) vi += t;
             }
             s_w[lane] = vi - v;                                   // exclusive offset of each warp
             if (lane == 31) s_tot = vi;
         }
         __syncthreads();
-        uint64_t run = s_carry + s_w[warp] + incl - sum;
+        ACC run = s_carry + s_w[warp] + incl - sum;
         if (i0 + E <= n) {
             uint32_t o[E];
 #pragma unroll
-            for (int k = 0; k < E; k++) { o[k] = run > 0xffffffffull ? 0xffffffffu : (uint32_t)run; run += c[k]; }
+            for (int k = 0; k < E; k++) { o[k] = (sizeof(ACC) > 4 && (uint64_t)run > 0xffffffffull) ? 0xffffffffu : (uint32_t)run; run += c[k]; }
             uint4 *p4 = reinterpret_cast<uint4 *>(bases + i0);
 #pragma unroll
             for (int q = 0; q < E / 4; q++) p4[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         } else {
 #pragma unroll
             for (int k = 0; k < E; k++) {
-                if (i0 + k < n) bases[i0 + k] = run > 0xffffffffull ? 0xffffffffu : (uint32_t)run;
+                if (i0 + k < n) bases[i0 + k] = (sizeof(ACC) > 4 && (uint64_t)run > 0xffffffffull) ? 0xffffffffu : (uint32_t)run;
                 run += c[k];
             }
         }
