@@ -820,6 +820,12 @@ extern "C" ws_status ws_renderer_create(ws_context *ctx, ws_format fmt, uint32_t
     r->grid_pre = ctx->sm_count * preprocess_blocks_per_sm(r->compressed);
     r->grid_sort = ctx->sm_count * sort_pass_blocks_per_sm();
     r->grid_bin = ctx->sm_count * binning_blocks_per_sm();
+    {   // A/B knobs (profiles/): fewer resident CTAs per SM for the persistent kernels leave room for the other frame's kernels
+        auto per_sm = [&](const char *name, int cur) { const char *e = getenv(name); const int k = e ? atoi(e) : 0; return (k >= 1 && k * ctx->sm_count < cur) ? k * ctx->sm_count : cur; };
+        r->grid_pre = per_sm("WS_PRE_CTAS_PER_SM", r->grid_pre);
+        r->grid_sort = per_sm("WS_SORT_CTAS_PER_SM", r->grid_sort);
+        r->grid_bin = per_sm("WS_BIN_CTAS_PER_SM", r->grid_bin);
+    }
     // 4 digit passes for both layouts: the compressed shader's "24-bit" key
     // (preprocess_compressed.wgsl:325) exceeds 0xffffff whenever clip.z < znear
     r->depth_passes = 4;
