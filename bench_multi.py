@@ -212,7 +212,9 @@ def run(args):
             "e2e": {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 480 * world, "d2h_bytes_per_step": W * H * 8,
                     "checksum": checksum, "checksum_what": "CRC-32 of the full RGBA16F frame of view %d, assembled from the %d ranks' bands and downloaded on rank 0" % (bench.CHECKSUM_VIEW, world),
                     "checksum_n1_same_view": checksum_n1, "checksum_matches_n1": checksum == checksum_n1},
-            "gpu_launches": K * world * (17 + (2 if depth > 1 else 0)),     # per rank and frame: 3 stage-1 + 3 routing (+2 gates) + 1 finish/histogram + 6 onesweep + 3 binning + 1 composite
+            # per rank and frame: epoch 1 + stage 1 3 + routing 3 (+ 2 gate kernels with several frames in flight) + finish / histogram 1 +
+            # depth passes 4 + per depth slab (binning 3 + tile passes 2 + composite 1); + the root's wait for the bands
+            "gpu_launches": K * (world * (12 + (2 if depth > 1 else 0) + (2 if (N // world) >= 2_000_000 else 1) * 6) + 1),
             "clocks": clocks,
         }
         sys.stdout.flush()
