@@ -866,7 +866,7 @@ extern "C" ws_status ws_renderer_set_occlusion_split(ws_renderer *r, int32_t ena
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// occlusion split: percentage of the depth-sorted splats that form the near slab (WS_SPLIT_NEAR_PCT; 0 / unset = half)
+// occlusion split: percentage of the depth-sorted splats that form the near slab (WS_SPLIT_NEAR_PCT; 0 / unset = the default, a quarter)
 static uint32_t split_near_pct()
 {
     static const uint32_t v = [] { const char *e = getenv("WS_SPLIT_NEAR_PCT"); const int p_ = e ? atoi(e) : 0; return (p_ >= 5 && p_ <= 95) ? (uint32_t)p_ : 0u; }();

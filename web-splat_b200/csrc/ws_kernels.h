@@ -71,7 +71,7 @@ struct BinningArgs {
     uint32_t *keep4;              // slab 2: ceil(V/2/4) words, one byte per splat: count kernel -> expand kernel
     uint32_t pair_cap;            // capacity of pair_tiles / pair_slots for this launch
     uint32_t *num_pairs_out;      // device counter that receives the number of pairs of this launch
-    uint32_t near_pct;            // occlusion split: share of the depth-sorted splats in the near slab, in percent (0 = half)
+    uint32_t near_pct;            // occlusion split: share of the depth-sorted splats in the near slab, in percent (0 = the default quarter)
     uint32_t num_tiles_hint;      // host-known number of tiles (sizes the shared-memory copy of tile_done); 0 = unknown
     uint32_t done_in_smem;        // set by launch_binning
 };
