@@ -153,6 +153,11 @@ impl GaussianRenderer {
         Ok(Self { h, format: color_format })
     }
     /// `prepare` (src/renderer.rs:191): enqueues stage 1 + 2 on `stream`.
+    ///
+    /// Everything is asynchronous, so a frame that turns out incomplete on the device (pair capacity exceeded, internal
+    /// error flag) cannot fail the call that enqueued it: the NEXT `prepare` that finds the earlier frame's status copy
+    /// completed returns that frame's error once (`PairOverflow` / `Cuda`) and enqueues nothing; calling it again proceeds.
+    /// `stats()` reports (and consumes) the status of the frame it synchronises.
     pub fn prepare(&mut self, stream: Stream, pc: &PointCloud, render_settings: &SplattingArgs) -> Result<()> {
         let a = ffi::ws_splatting_args::from(render_settings);
         check(unsafe { ffi::ws_renderer_prepare(self.h, pc.h, &a, stream.0) })

@@ -183,7 +183,10 @@ public:
     GaussianRenderer(const GaussianRenderer &) = delete;
     GaussianRenderer &operator=(const GaussianRenderer &) = delete;
 
-    /// prepare (renderer.rs:191): enqueues stage 1 + 2 on the caller's stream (cudaStream_t as void*)
+    /// prepare (renderer.rs:191): enqueues stage 1 + 2 on the caller's stream (cudaStream_t as void*).
+    /// Throws ws::Error(WS_ERR_PAIR_OVERFLOW / WS_ERR_CUDA) ONCE when an EARLIER frame of this renderer turned out incomplete
+    /// on the device (everything is asynchronous: the frame that overflowed could not fail its own call); nothing is enqueued
+    /// by the throwing call, the next one proceeds.  stats() reports the status of the frame it synchronises.
     void prepare(void *stream, const PointCloud &pc, const SplattingArgs &render_settings)
     {
         const ws_splatting_args a = render_settings.c();
