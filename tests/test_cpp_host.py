@@ -185,3 +185,63 @@ def test_cpp_readers_survive_damaged_input(ws, tool, tmp_path):
         victim.write_bytes(bytes(b))
         p = subprocess.run([tool, flag, str(victim)], capture_output=True, timeout=60)
         assert p.returncode in (0, 1), (flag, p.returncode, p.stderr[-200:])
+
+
+def test_cpp_npz_reader_rejects_hostile_sizes(ws, tool, tmp_path):
+    """The attacker-controlled fields the advisor named (tools/npz_reader.hpp): a .npy shape whose byte count
+    wraps (2^63, 2), a central-directory name / extra length that runs past the file, a local-header offset and a compressed
+    size near 2^64 (zip64), an implausible uncompressed size.  Each must end in the reader's own error (exit 1), never in a
+    crash, a hang or a huge allocation."""
+    import io
+    import struct
+    import zipfile
+
+    def npy(shape_text, payload=b"\x00" * 16, descr="<f4"):
+        hdr = ("{'descr': '%s', 'fortran_order': False, 'shape': %s, }" % (descr, shape_text)).encode()
+        hdr += b" " * ((64 - (10 + len(hdr) + 1) % 64) % 64) + b"\n"
+        return b"\x93NUMPY\x01\x00" + struct.pack("<H", len(hdr)) + hdr + payload
+
+    def run(blob):
+        f = tmp_path / "h.npz"; f.write_bytes(blob)
+        p = subprocess.run([tool, "--parse-npz", str(f)], capture_output=True, text=True, timeout=60)
+        assert p.returncode == 1 and "npz:" in p.stderr, (p.returncode, p.stderr[-300:])
+
+    def zip_of(name, data):
+        bio = io.BytesIO()
+        with zipfile.ZipFile(bio, "w", zipfile.ZIP_STORED) as z:
+            z.writestr(name, data)
+        return bytearray(bio.getvalue())
+
+    # (1) shapes whose element count times the item size wraps around 2^64, or simply exceeds the member
+    for shape in ("(9223372036854775808, 2)", "(4294967296, 4294967296)", "(1000000,)", "(18446744073709551615,)"):
+        run(bytes(zip_of("xyz.npy", npy(shape))))
+    good = zip_of("xyz.npy", npy("(4,)"))
+    cd = good.rfind(b"PK\x01\x02"); eocd = good.rfind(b"PK\x05\x06")
+    assert cd > 0 and eocd > cd
+    # (2) file-name / extra-field lengths of the central directory entry running past the end of the file
+    for off in (28, 30, 32):
+        b = bytearray(good); b[cd + off:cd + off + 2] = b"\xff\xff"; run(bytes(b))
+    # (3) local header offset and sizes forced through the zip64 extra field to values near 2^64
+    b = bytearray(good)
+    extra = struct.pack("<HHQQQ", 1, 24, 0xfffffffffffffff0, 0xfffffffffffffff0, 0xfffffffffffffff0)
+    entry_end = cd + 46 + struct.unpack("<H", b[cd + 28:cd + 30])[0]
+    b[cd + 20:cd + 28] = b"\xff" * 8                          # compressed + uncompressed size = 0xffffffff -> "see zip64 extra"
+    b[cd + 42:cd + 46] = b"\xff" * 4                          # local header offset likewise
+    b[cd + 30:cd + 32] = struct.pack("<H", len(extra))
+    b[entry_end:entry_end] = extra
+    run(bytes(b))
+    # (4) a zip64 extra field shorter than the values it must hold
+    b2 = bytearray(good)
+    short = struct.pack("<HHQ", 1, 8, 5)
+    b2[cd + 20:cd + 28] = b"\xff" * 8; b2[cd + 42:cd + 46] = b"\xff" * 4
+    b2[cd + 30:cd + 32] = struct.pack("<H", len(short)); b2[entry_end:entry_end] = short
+    run(bytes(b2))
+    # (5) central directory offset / entry count beyond the file
+    b3 = bytearray(good); b3[eocd + 16:eocd + 20] = struct.pack("<I", 0x7fffffff); run(bytes(b3))
+    b4 = bytearray(good); b4[eocd + 10:eocd + 12] = struct.pack("<H", 60000); run(bytes(b4))
+    # (6) a stored member that claims a different uncompressed size
+    b5 = bytearray(good); b5[cd + 24:cd + 28] = struct.pack("<I", 0x70000000); run(bytes(b5))
+    # and the untouched archive still parses
+    f = tmp_path / "ok.npz"; f.write_bytes(bytes(good))
+    p = subprocess.run([tool, "--parse-npz", str(f)], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and p.stdout.startswith("xyz <f4 4"), p.stderr
